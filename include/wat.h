@@ -1,0 +1,125 @@
+/* libwat — C ABI of the B200-native Whisper-AT tagging path.
+ *
+ * The reference (chat-prompt/whisper-at) is pure Python and has no FFI; its boundary for this path is the
+ * Python API.  Each entry point below replaces the arithmetic behind one reference call so a
+ * maintainer can bind it with ctypes:
+ *
+ *   wat_logmel      <- whisper_at.audio.log_mel_spectrogram        package/whisper-at/whisper_at/audio.py:110-157
+ *   wat_encoder     <- AudioEncoder.forward (x, all_x)             package/whisper-at/whisper_at/model.py:156-177
+ *   wat_tltr        <- ATModel.forward                             package/whisper-at/whisper_at/model.py:351-379
+ *   wat_tag         <- the per-window body of transcribe()         package/whisper-at/whisper_at/transcribe.py:127,241-263
+ *   wat_tag_host    <- same, host buffers in / host logits out (what a non-torch caller binds)
+ *   wat_create / wat_set_weight / wat_finalize  <- Whisper.__init__ + load_state_dict   model.py:224-246, __init__.py:184-191
+ *
+ * Conventions: plain pointers and sizes only; device pointers are owned by the caller (e.g. torch tensors);
+ * `stream` is a cudaStream_t passed as void*; every function returns 0 on success or a negative wat_status,
+ * and wat_last_error() returns a thread-local message.  No C++ exception crosses the boundary.  A handle is
+ * bound to the CUDA device that was current at wat_create and is not re-entrant (one handle per thread/stream).
+ * There is no CPU fallback: without a CUDA device every compute call returns WAT_ERR_CUDA.
+ */
+#ifndef WAT_H_
+#define WAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WAT_API __attribute__((visibility("default")))
+#else
+#define WAT_API
+#endif
+
+typedef struct wat_handle wat_handle;
+
+enum wat_status {
+  WAT_OK = 0,
+  WAT_ERR_INVALID = -1,   /* bad argument / shape (the reference raises AssertionError / RuntimeError) */
+  WAT_ERR_CUDA = -2,      /* CUDA runtime or driver error, or no device */
+  WAT_ERR_STATE = -3,     /* wrong call order: weights missing, not finalized */
+  WAT_ERR_NOMEM = -4
+};
+
+enum wat_precision {
+  WAT_FP32 = 0,           /* every contraction in fp32 SIMT FMA: the correctness mode (logits within 1e-3) */
+  WAT_BF16 = 1            /* bf16 operands, fp32 accumulate on tcgen05 tensor cores; fp32 residual stream */
+};
+
+typedef struct wat_config {
+  int32_t n_mels;         /* 80 or 128 */
+  int32_t n_audio_ctx;    /* 1500 */
+  int32_t n_audio_state;  /* d */
+  int32_t n_audio_head;   /* d / 64 */
+  int32_t n_audio_layer;  /* L */
+  int32_t at_low_compute; /* 0: tl_tr_1_8, 1: tl_down_tr_512_1_8  (model.py:243-246) */
+  int32_t at_dim;         /* 512 when at_low_compute, ignored otherwise */
+  int32_t n_class;        /* 527 */
+  int32_t precision;      /* enum wat_precision */
+  int32_t max_batch;      /* clips processed per internal chunk (workspace is sized for this); 0 = default */
+} wat_config;
+
+WAT_API int wat_abi_version(void);
+WAT_API const char* wat_last_error(void);
+
+/* Model lifetime.  Weights are passed by their reference state_dict key ("encoder.blocks.0.attn.query.weight",
+ * "at_model.time_tr.mlp.0.bias", ...), as contiguous fp32 HOST arrays; decoder.* keys are accepted and ignored. */
+WAT_API int wat_create(const wat_config* cfg, wat_handle** out);
+WAT_API int wat_set_weight(wat_handle* h, const char* key, const float* host_data, int64_t numel);
+WAT_API int wat_finalize(wat_handle* h);   /* checks every tensor of the tagging path is present, packs for the device */
+WAT_API int wat_destroy(wat_handle* h);
+
+/* log-mel of B clips.  pcm: device fp32, clip c at pcm + c*clip_stride; n_valid (HOST int32[B] or NULL = all
+ * n_samples) real samples per clip, `n_pad` zero samples appended (the reference's `padding`); the first
+ * n_frames frames are written to mel_out [B, n_mels, n_frames] fp32 (the reference's layout).  The `max - 8`
+ * clamp spans the whole padded signal of a clip (clamp_scope 0: one call of the reference per clip) or the
+ * whole batch (clamp_scope 1: what the reference computes when handed a 2-D tensor, audio.py:155).
+ * Needs no weights: valid on a handle that has not been finalized. */
+WAT_API int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+               int32_t n_pad, int32_t B, int32_t n_frames, int32_t clamp_scope, float* mel_out, void* stream);
+
+/* encoder: mel [B, n_mels, 3000] fp32 device -> pooled_out [B, L, 75, d] fp32 (every clip, not only clip 0);
+ * x_out (may be NULL) [B, 1500, d] fp32 = ln_post(x). */
+WAT_API int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* pooled_out, float* x_out, void* stream);
+
+/* TL-TR head on pooled[:, :, t_start:t_start+t_len, :] of a [B, L, t_total, d] fp32 device tensor with decision
+ * window dw = int(at_time_res * 2.5); logits_out [B, ceil(t_len/dw), n_class] fp32 device. */
+WAT_API int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int32_t t_start, int32_t t_len,
+             int32_t dw, float* logits_out, void* stream);
+
+/* fused mel -> encoder -> head for B clips of <= 480000 samples; logits_out [B, ceil(75/dw), n_class] device */
+WAT_API int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+            int32_t B, int32_t dw, float* logits_out, void* stream);
+
+/* same with HOST buffers (pinned or pageable): copies in, computes, copies logits out, synchronises */
+WAT_API int wat_tag_host(wat_handle* h, const float* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                 int32_t B, int32_t dw, float* logits_host);
+
+/* introspection */
+WAT_API int64_t wat_workspace_bytes(const wat_handle* h);
+WAT_API int64_t wat_kernel_launches(const wat_handle* h);   /* kernels launched by this handle since creation */
+WAT_API int wat_num_sms(const wat_handle* h);
+
+/* per-kernel-class device timing: when enabled every kernel launch of the handle is bracketed by CUDA events on
+ * the launching stream; wat_profile_read synchronises, sums the elapsed ms and launch counts per class
+ * (arrays of wat_profile_classes() entries) and clears the records. */
+WAT_API int wat_profile(wat_handle* h, int32_t enable);
+WAT_API int wat_profile_classes(void);
+WAT_API const char* wat_profile_class_name(int32_t i);
+WAT_API int wat_profile_read(wat_handle* h, double* ms, int64_t* launches);
+
+/* unit-test hooks for single kernels (device pointers; fp32 in/out, converted internally when tc != 0) */
+WAT_API int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float* R, float* C, int32_t M, int32_t N,
+                 int32_t K, int32_t act, int32_t tc, void* stream);
+/* x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D]: fused-QKV GEMM + encoder self-attention (hd 64) */
+WAT_API int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
+                      int32_t n_head, int32_t tc, void* stream);
+WAT_API int wat_dbg_tma_overlap_probe(void);   /* 1 if the driver accepts a tensor map whose row stride < row length */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAT_H_ */

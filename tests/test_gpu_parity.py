@@ -1,0 +1,352 @@
+"""GPU parity: the CUDA path (through libwat's C ABI) against the CPU oracle on seeded inputs and against
+the fixtures the real reference produced (tests/golden).  Tolerances are BASELINE.json's:
+log-mel 1e-4 relative (|a-b| <= 1e-4*max(1,|ref|)), fp32-mode logits 1e-3 max-abs, bf16-mode logits 3e-2
+max-abs with identical top-5 labels per window (tie-aware: a swap only counts when the reference's own gap
+between the swapped logits exceeds 2x the measured error)."""
+import ctypes as C
+import math
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import wat_oracle as O
+import whisper_at
+from whisper_at import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+MEL_COLS = np.r_[0:40, 1480:1520, 2960:3000, 40:2960:73]
+TOL_MEL, TOL_FP32, TOL_BF16 = 1e-4, 1e-3, 3e-2
+
+
+def rel_err(a, ref):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    ref = torch.as_tensor(ref, dtype=torch.float64).cpu()
+    return float(((a - ref).abs() / ref.abs().clamp(min=1.0)).max())
+
+
+def max_abs(a, ref):
+    return float((torch.as_tensor(a).cpu().double() - torch.as_tensor(ref).cpu().double()).abs().max())
+
+
+def top5_consistent(ours, ref, err):
+    """identical top-5 label sets per window, ignoring swaps across a reference gap smaller than 2*err"""
+    ours, ref = torch.as_tensor(ours).cpu().reshape(-1, 527), torch.as_tensor(ref).cpu().reshape(-1, 527)
+    for o, r in zip(ours, ref):
+        so, sr = set(torch.topk(o, 5).indices.tolist()), set(torch.topk(r, 5).indices.tolist())
+        if so == sr:
+            continue
+        kth = torch.topk(r, 5).values[-1]
+        for idx in so ^ sr:
+            if abs(float(r[idx] - kth)) > 2 * max(err, 1e-6):
+                return False
+    return True
+
+
+_models = {}
+
+
+def model_for(name, n_mels=80, low=False, seed=0, init="default", precision="fp32", max_batch=16):
+    key = (name, n_mels, low, seed, init, precision)
+    if key not in _models:
+        d, h, L = synth.MODEL_SHAPES[name]
+        dims = whisper_at.ModelDimensions(n_mels, 1500, d, h, L, 51865, 448, d, h, L)
+        m = whisper_at.Whisper(dims, at_low_compute=low, precision=precision, max_batch=max_batch)
+        sd = synth.synth_state_dict(n_mels, d, L, low, seed=seed, init=init)
+        m.load_state_dict(sd, strict=False)
+        _models[key] = (m.to("cuda"), sd, h)
+    return _models[key]
+
+
+def golden(golden_dir, tag):
+    return np.load(os.path.join(golden_dir, tag + ".npz"), allow_pickle=True)
+
+
+# ------------------------------------------------------------------------------------------ mel front end
+def test_mel_known_answers(golden_dir):
+    z = golden(golden_dir, "mel_kat")
+    sil = whisper_at.log_mel_spectrogram(torch.zeros(480000), padding=480000)[:, :3000]
+    assert sil.shape == (80, 3000) and torch.all(sil == float(z["silence_value"]))
+    t = torch.arange(480000) / 16000.0
+    m = whisper_at.log_mel_spectrogram(0.5 * torch.sin(2 * math.pi * 1000.0 * t), padding=480000)[:, :3000]
+    assert int(m[:, 100].argmax()) == int(z["tone1k_argmax_bin"])
+    assert rel_err(m[:, 100], z["tone1k_col100"]) <= TOL_MEL
+    assert float(m.max() - m.min()) <= 2.0 + 1e-6
+    short = synth.synth_clip(2)[:80000]
+    ms = whisper_at.log_mel_spectrogram(short, padding=480000)[:, :3000]
+    assert rel_err(ms[:, MEL_COLS], z["short5s_cols"]) <= TOL_MEL
+
+
+@pytest.mark.parametrize("ci", [0, 1, 7])
+def test_mel_vs_reference_fixture(golden_dir, ci):
+    z = golden(golden_dir, "tiny_default")
+    clip = synth.synth_clip(ci)
+    m = whisper_at.log_mel_spectrogram(clip.cuda(), padding=480000)
+    assert m.is_cuda and m.shape == (80, 6000)
+    m = m[:, :3000].cpu()
+    assert rel_err(m[:, MEL_COLS], z[f"mel_c{ci}"]) <= TOL_MEL
+    assert abs(float(m.max()) - float(z[f"mel_c{ci}_max"])) <= 1e-5
+    assert abs(float(m.double().sum()) - float(z[f"mel_c{ci}_sum"])) <= 0.05      # checksum over all 240k values
+
+
+def test_mel_vs_oracle_all_columns_and_fp64_truth():
+    for ci in (2, 5, 15):
+        clip = synth.synth_clip(ci)
+        m = whisper_at.log_mel_spectrogram(clip, padding=480000)[:, :3000]
+        assert rel_err(m, O.log_mel_clip(clip)) <= TOL_MEL
+        truth = O.log_mel_clip(clip, dtype=torch.float64, explicit_dft=True)
+        assert rel_err(m, truth) <= TOL_MEL                                      # we are closer to fp64 than the fp32 FFT is
+
+
+def test_mel_unpadded_and_batched_and_128(golden_dir):
+    clip = synth.synth_clip(1)
+    a = whisper_at.log_mel_spectrogram(clip)                                     # padding=0: right edge is reflected
+    assert a.shape == (80, 3000)
+    assert rel_err(a, O.log_mel(clip)) <= TOL_MEL
+    two = torch.stack([synth.synth_clip(3) * 0.01, synth.synth_clip(4)])
+    b = whisper_at.log_mel_spectrogram(two)                                      # 2-D: ONE clamp floor for the batch
+    ref = torch.stack([O.stft_power(x) for x in two])
+    fb = torch.from_numpy(O.mel_filterbank(80))
+    ls = torch.clamp(fb @ ref, min=1e-10).log10()
+    ls = (torch.maximum(ls, ls.max() - 8.0) + 4.0) / 4.0
+    assert b.shape == (2, 80, 3000) and rel_err(b, ls) <= TOL_MEL
+    z = golden(golden_dir, "large_v2_m128_lively")
+    m128 = whisper_at.log_mel_spectrogram(clip, n_mels=128, padding=480000)[:, :3000]
+    assert m128.shape == (128, 3000) and rel_err(m128[:, MEL_COLS], z["mel_c1"]) <= TOL_MEL
+    with pytest.raises(AssertionError, match="Unsupported n_mels: 64"):
+        whisper_at.log_mel_spectrogram(clip, n_mels=64)
+
+
+# ------------------------------------------------------------------------------------------ single kernels
+def _dbg_gemm(A, W, bias, R, act, tc):
+    L = _lib.lib()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), device="cuda", dtype=torch.float32)
+    _lib.check(L.wat_dbg_gemm(A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                              R.data_ptr() if R is not None else None, out.data_ptr(), M, N, K, act, tc,
+                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [(128, 256, 64, 0, False), (300, 384, 240, 1, False), (1500, 1280, 1280, 0, True),
+                                           (4097, 512, 2048, 1, True), (77, 128, 384, 0, False)])
+@pytest.mark.parametrize("tc", [0, 1], ids=["simt", "tcgen05"])
+def test_gemm_kernels_vs_torch(tc, M, N, K, act, res):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    R = torch.randn(M, N, generator=g).cuda() if res else None
+    out = _dbg_gemm(A, W, bias, R, act, tc)
+    if tc:
+        A, W = A.bfloat16().float(), W.bfloat16().float()                        # the kernel's operand rounding
+    ref = A.double() @ W.double().T + bias.double()
+    if act:
+        ref = 0.5 * ref * (1 + torch.erf(ref / math.sqrt(2)))
+    if res:
+        ref = ref + R.double()
+    assert max_abs(out, ref) <= (2e-4 if tc else 1e-4) * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 128, 2), (2, 1500, 6), (3, 200, 4)])
+@pytest.mark.parametrize("tc", [0, 1], ids=["simt", "tcgen05"])
+def test_attention_kernels_vs_torch(tc, B, T, H):
+    D = 64 * H
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+    x = torch.randn(B * T, D, generator=g).cuda()
+    w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D) * 2.0).cuda()
+    b = torch.randn(3 * D, generator=g).cuda()
+    out = torch.empty(B * T, D, device="cuda")
+    _lib.check(_lib.lib().wat_dbg_attention(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), B, T, H, tc,
+                                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    xd, wd = (x.bfloat16().double(), w.bfloat16().double()) if tc else (x.double(), w.double())
+    qkv = xd @ wd.T + b.double()
+    if tc:
+        qkv = qkv.bfloat16().double()
+    q, k, v = [t.reshape(B, T, H, 64).permute(0, 2, 1, 3) for t in qkv.split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * T, D)
+    assert max_abs(out, ref) <= (2e-2 if tc else 1e-4) * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------ encoder + head, fp32 mode
+@pytest.mark.parametrize("tag,init,seed,clips,resolutions,starts", [
+    ("tiny_default", "default", 0, (0, 1, 7), (10, 2, 0.4, 4, 30), (0,)),
+    ("tiny_lively", "lively", 1, (1, 7), (10, 4), (0, 10)),
+])
+def test_tiny_fp32_vs_reference_fixtures(golden_dir, tag, init, seed, clips, resolutions, starts):
+    z = golden(golden_dir, tag)
+    m, sd, h = model_for("tiny", seed=seed, init=init, precision="fp32")
+    for ci in clips:
+        clip = synth.synth_clip(ci)
+        mel = whisper_at.log_mel_spectrogram(clip.cuda(), padding=480000)[:, :3000]
+        x, all_x = m.encoder(mel[None])
+        assert x.shape == (1, 1500, 384) and all_x.shape == (4, 75, 384)
+        ref = torch.from_numpy(z[f"pooled_c{ci}"])
+        assert max_abs(all_x[:, ::5, ::3], ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+        for res in resolutions:
+            for a0 in starts:
+                lg = m.at_model(all_x[:, a0:, :], time_resolution=res)
+                refl = z[f"logits_c{ci}_r{res}_a{a0}"]
+                assert tuple(lg.shape) == refl.shape
+                assert max_abs(lg, refl) <= TOL_FP32, (ci, res, a0)
+
+
+def test_encoder_x_output_and_wrong_shape():
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="fp32")
+    clip = synth.synth_clip(1)
+    mel = O.log_mel_clip(clip)
+    x, all_x = m.encoder(mel[None].cuda())
+    pooled_o, x_o = O.encoder_pooled(mel[None], sd, h, return_x=True)
+    assert max_abs(all_x, pooled_o[0]) <= 1e-3 * max(1.0, float(pooled_o.abs().max()))
+    assert max_abs(x, x_o) <= 2e-3
+    with pytest.raises(AssertionError, match="incorrect audio shape"):
+        m.encoder(torch.zeros(1, 80, 2000).cuda())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_tiny_low_and_base_batch_vs_reference_fixtures(golden_dir, precision, tol):
+    z = golden(golden_dir, "tiny_low_lively")
+    m, sd, h = model_for("tiny", low=True, seed=1, init="lively", precision=precision)
+    clip = synth.synth_clip(1)
+    for res in (10, 2, 4):
+        lg = m.tag_batch(clip[None].cuda(), at_time_res=res)[0]
+        ref = z[f"logits_c1_r{res}_a0"]
+        err = max_abs(lg, ref)
+        assert err <= tol, (res, err)
+        assert top5_consistent(lg, ref, err)
+    # base, batch of 2 clips in ONE call: every clip equals the reference run on it alone
+    z = golden(golden_dir, "base_lively")
+    m, sd, h = model_for("base", seed=1, init="lively", precision=precision)
+    lg = m.tag_batch(synth.synth_batch(2).cuda(), at_time_res=10)
+    for ci in (0, 1):
+        ref = z[f"logits_c{ci}_r10_a0"]
+        err = max_abs(lg[ci], ref)
+        assert err <= tol, (ci, err)
+        assert top5_consistent(lg[ci], ref, err)
+
+
+def test_tiny_bf16_vs_reference_fixtures(golden_dir):
+    for tag, init, seed, clips, ress in (("tiny_default", "default", 0, (0, 1, 7), (10, 2, 0.4, 4, 30)),
+                                         ("tiny_lively", "lively", 1, (1, 7), (10, 4))):
+        z = golden(golden_dir, tag)
+        m, sd, h = model_for("tiny", seed=seed, init=init, precision="bf16")
+        for ci in clips:
+            for res in ress:
+                lg = m.tag_batch(synth.synth_clip(ci)[None].cuda(), at_time_res=res)[0]
+                ref = z[f"logits_c{ci}_r{res}_a0"]
+                err = max_abs(lg, ref)
+                assert err <= TOL_BF16, (tag, ci, res, err)
+                assert top5_consistent(lg, ref, err)
+
+
+@pytest.mark.parametrize("tag,name,n_mels,low,ress", [("small_low_lively", "small", 80, True, (2, 10)),
+                                                      ("medium_low_lively", "medium", 80, True, (10,)),
+                                                      ("large_v2_m128_lively", "large-v2", 128, False, (10,))])
+def test_baseline_configs_bf16_vs_reference_fixtures(golden_dir, tag, name, n_mels, low, ress):
+    """configs[2..4] of BASELINE.json at their real model sizes; the reference's logits come from the fixtures."""
+    z = golden(golden_dir, tag)
+    m, sd, h = model_for(name, n_mels=n_mels, low=low, seed=1, init="lively", precision="bf16")
+    batch = torch.stack([synth.synth_clip(1), synth.synth_clip(2), synth.synth_clip(1)]).cuda()
+    for res in ress:
+        lg = m.tag_batch(batch, at_time_res=res)
+        ref = z[f"logits_c1_r{res}_a0"]
+        err = max_abs(lg[0], ref)
+        assert err <= TOL_BF16, (tag, res, err)
+        assert top5_consistent(lg[0], ref, err)
+        assert torch.equal(lg[0], lg[2])                       # same clip at two batch positions: bit-identical
+        assert not torch.equal(lg[0], lg[1])
+    _models.clear()
+    torch.cuda.empty_cache()
+
+
+def test_fp32_large_config_vs_reference_fixture(golden_dir):
+    z = golden(golden_dir, "small_low_lively")
+    m, sd, h = model_for("small", low=True, seed=1, init="lively", precision="fp32")
+    lg = m.tag_batch(synth.synth_clip(1)[None].cuda(), at_time_res=2)[0]
+    assert max_abs(lg, z["logits_c1_r2_a0"]) <= TOL_FP32
+    _models.clear()
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------ API level
+def test_transcribe_matches_reference_audio_tag(golden_dir):
+    z = golden(golden_dir, "api_tiny")
+    m, sd, h = model_for("tiny", seed=0, init="lively", precision="fp32")
+    for ci, res in ((1, 10), (3, 2), (1, 0.8)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = m.transcribe(synth.synth_clip(ci).numpy(), at_time_res=res, language="en", fp16=False)
+        ref = z[f"audio_tag_c{ci}_r{res}"]
+        assert r["audio_tag"].shape == ref.shape and r["audio_tag"].device.type == "cpu"
+        assert max_abs(r["audio_tag"], ref) <= TOL_FP32
+        assert r["at_time_res"] == res and r["language"] == "en"
+        parsed = whisper_at.parse_at_label(r, language="en", top_k=5, p_threshold=-10)
+        names = [[p[0] for p in row["audio tags"]] for row in parsed]
+        ref_names = [list(row) for row in z[f"top5_c{ci}_r{res}"]]
+        assert len(names) == len(ref_names)
+        assert sum(set(a) == set(b) for a, b in zip(names, ref_names)) >= len(names) - 1   # ties: see top5_consistent
+    with pytest.raises(AssertionError, match="integer multiple of 0.4 second"):
+        m.transcribe(synth.synth_clip(1).numpy(), at_time_res=0.5)
+    # bf16 path through the same API (default fp16=True in the reference -> bf16 here)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r16 = m.transcribe(synth.synth_clip(1), at_time_res=10)
+    assert max_abs(r16["audio_tag"], z["audio_tag_c1_r10"]) <= TOL_BF16
+
+
+def test_transcribe_long_file_fixed_stride_windows():
+    """70 s file -> 3 windows through the encoder as one batch; rows are placed with the reference's
+    at_start / floor(seek / window) arithmetic (transcribe.py:255-263)."""
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="fp32")
+    audio = torch.cat([synth.synth_clip(1), synth.synth_clip(2), synth.synth_clip(3)[:160000]])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = m.transcribe(audio, at_time_res=4, fp16=False)
+    content_frames = audio.shape[0] // 160
+    assert r["audio_tag"].shape == (math.ceil(content_frames / 400), 527)
+    mel = O.log_mel(audio, 80, padding=480000)
+    expect = torch.zeros_like(r["audio_tag"])
+    for seek in range(0, content_frames, 3000):
+        pooled = O.encoder_pooled(mel[None, :, seek:seek + 3000], sd, h)
+        a0 = math.floor(seek % 400 / 40)
+        tag = O.tltr_head(pooled[:, :, a0:, :], sd, 4)[0]
+        s0 = seek // 400
+        e0 = min(expect.shape[0], s0 + tag.shape[0])
+        expect[s0:e0] = tag[:e0 - s0]
+    assert max_abs(r["audio_tag"], expect) <= TOL_FP32
+
+
+def test_host_buffer_entry_point_and_launch_counter():
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="bf16")
+    a = synth.synth_batch(3, start=1)
+    dev = m.tag_batch(a.cuda(), at_time_res=10).cpu()
+    n0 = m.kernel_launches()
+    host = m.tag_batch_host(a.pin_memory(), at_time_res=10)
+    assert m.kernel_launches() > n0
+    assert torch.equal(dev, host)
+    assert host.shape == (3, 3, 527)
+
+
+def test_permutation_and_chunking_invariance():
+    """size-independent properties: clip order and internal chunking (max_batch) do not change any clip's logits"""
+    a = synth.synth_batch(5, start=1).cuda()
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="bf16", max_batch=16)
+    base = m.tag_batch(a, at_time_res=2)
+    perm = torch.tensor([3, 0, 4, 1, 2], device="cuda")
+    assert torch.equal(m.tag_batch(a[perm], at_time_res=2), base[perm])
+    d, hh, L = synth.MODEL_SHAPES["tiny"]
+    dims = whisper_at.ModelDimensions(80, 1500, d, hh, L, 51865, 448, d, hh, L)
+    m2 = whisper_at.Whisper(dims, precision="bf16", max_batch=2)
+    m2.load_state_dict(sd, strict=False)
+    m2 = m2.to("cuda")
+    assert torch.equal(m2.tag_batch(a, at_time_res=2), base)
+    nv = np.array([480000, 80000, 480000, 123456, 480000], dtype=np.int32)
+    short = m.tag_batch(a, at_time_res=10, n_valid=nv)
+    one = m.tag_batch(a[1:2, :80000].contiguous(), at_time_res=10)
+    assert torch.equal(short[1], one[0])

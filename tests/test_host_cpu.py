@@ -1,0 +1,149 @@
+"""CPU: host-side logic of the drop-in package and the C-ABI surface (no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import whisper_at
+from whisper_at import _lib, synth
+from whisper_at.transcribe import check_at_time_res
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "wat.h")).read()
+    declared = set(re.findall(r"WAT_API\s+[\w\s\*]+?\b(wat_\w+)\s*\(", hdr))
+    assert len(declared) >= 15
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (wat_\w+)", out))
+    assert declared <= exported
+    assert L.wat_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    L = _lib.lib()
+    cfg = _lib.WatConfig(80, 1500, 384, 6, 4, 0, 0, 527, 0, 0)
+    h = C.c_void_p()
+    assert L.wat_create(C.byref(cfg), C.byref(h)) == _lib.WAT_ERR_CUDA
+    assert b"no CPU fallback" in L.wat_last_error()
+    dims = whisper_at.ModelDimensions(80, 1500, 384, 6, 4, 51865, 448, 384, 6, 4)
+    m = whisper_at.Whisper(dims)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.encoder(torch.zeros(1, 80, 3000))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        whisper_at.log_mel_spectrogram(np.zeros(16000, np.float32))
+
+
+def test_config_validation_messages():
+    L = _lib.lib()
+    h = C.c_void_p()
+    bad = _lib.WatConfig(64, 1500, 384, 6, 4, 0, 0, 527, 0, 0)
+    assert L.wat_create(C.byref(bad), C.byref(h)) == _lib.WAT_ERR_INVALID
+    assert b"Unsupported n_mels: 64" in L.wat_last_error()          # the reference's assert text (audio.py:103)
+    bad = _lib.WatConfig(80, 1500, 400, 6, 4, 0, 0, 527, 0, 0)
+    assert L.wat_create(C.byref(bad), C.byref(h)) == _lib.WAT_ERR_INVALID
+
+
+def test_state_dict_keys_match_reference_names():
+    for low in (False, True):
+        dims = whisper_at.ModelDimensions(80, 1500, 384, 6, 4, 51865, 448, 384, 6, 4)
+        m = whisper_at.Whisper(dims, at_low_compute=low)
+        sd = synth.synth_state_dict(80, 384, 4, low)
+        assert set(m.state_dict()) == set(sd) | {"encoder.positional_embedding"}
+        for k, v in sd.items():
+            assert tuple(m.state_dict()[k].shape) == tuple(v.shape), k
+        # decoder.* keys of a full OpenAI checkpoint are accepted and dropped; strict otherwise
+        full = dict(sd)
+        full["decoder.token_embedding.weight"] = torch.zeros(4, 4)
+        full["encoder.positional_embedding"] = synth.sinusoid_table(1500, 384)
+        m.load_state_dict(full, strict=True)
+        bad = dict(sd)
+        bad.pop("at_model.mlp_layer.1.bias")
+        with pytest.raises(RuntimeError):
+            m.load_state_dict(bad, strict=True)
+    assert m.is_multilingual and m.device == torch.device("cpu")
+    # the TL-TR parameter counts the reference publishes (README.md:258-269)
+    def at_params(name, low):
+        d, _, L = synth.MODEL_SHAPES[name]
+        return sum(int(np.prod(s)) for k, s in synth.tagging_state_shapes(80, d, L, low).items() if k.startswith("at_model."))
+    assert abs(at_params("large-v2", False) / 1e6 - 40.03) < 0.01
+    assert abs(at_params("small", False) / 1e6 - 14.581) < 0.001
+    assert abs(at_params("small", True) / 1e6 - 6.970) < 0.001
+
+
+def test_load_model_errors():
+    with pytest.raises(RuntimeError, match="Model nonexistent not found; available models"):
+        whisper_at.load_model("nonexistent")
+    assert whisper_at.available_models()[0] == "tiny.en" and "large-v2" in whisper_at.available_models()
+    with pytest.raises(KeyError):
+        whisper_at.load_model("tiny", at_low_compute=True, download_root="/tmp/wat_none")   # no tiny_low head exists
+
+
+def test_at_time_res_validation_matches_reference():
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert check_at_time_res(10) == 1000                      # no warning at the trained resolution
+    for bad in (0.5, 1, 4.4, 8.8):                                # 4.4*100 == 440.00000000000006
+        with pytest.raises(AssertionError, match="must be an integer multiple of 0.4 second"):
+            check_at_time_res(bad)
+    with pytest.warns(UserWarning, match="Current at_time_res is 2.00 second"):
+        assert check_at_time_res(2) == 200
+    with pytest.warns(UserWarning):
+        check_at_time_res(0.4)
+
+
+def test_pad_or_trim():
+    a = np.arange(10, dtype=np.float32)
+    assert whisper_at.pad_or_trim(a, 4).tolist() == [0, 1, 2, 3]
+    assert whisper_at.pad_or_trim(a, 12).tolist() == list(range(10)) + [0, 0]
+    t = torch.arange(12.).reshape(2, 6)
+    assert whisper_at.pad_or_trim(t, 4).shape == (2, 4)
+    p = whisper_at.pad_or_trim(t, 8)
+    assert p.shape == (2, 8) and p[:, 6:].abs().sum() == 0 and torch.equal(p[:, :6], t)
+    p0 = whisper_at.pad_or_trim(t, 3, axis=0)
+    assert p0.shape == (3, 6) and torch.equal(p0[:2], t)
+    assert whisper_at.pad_or_trim(np.zeros((80, 2000)), 3000).shape == (80, 3000)
+
+
+def test_parse_at_label_matches_reference_fixture(golden_dir):
+    z = np.load(os.path.join(golden_dir, "api_tiny.npz"), allow_pickle=True)
+    g = torch.Generator().manual_seed(5)
+    fixed = torch.randn(4, 527, generator=g)
+    res = {"language": "en", "at_time_res": 4.8, "audio_tag": fixed}
+    p = whisper_at.parse_at_label(res, language="follow_asr", top_k=3, p_threshold=1.5, include_class_list=list(range(0, 527, 2)))
+    assert repr(p) == str(z["parse_fixed"])
+    p2 = whisper_at.parse_at_label(res, language="zh", top_k=2, p_threshold=-1)
+    assert repr(p2) == str(z["parse_fixed_zh"])
+    with pytest.warns(UserWarning, match="language not supported"):
+        p3 = whisper_at.parse_at_label(dict(res, language="xx"), top_k=1)
+    assert p3[0]["audio tags"][0][0] == whisper_at.parse_at_label(res, language="en", top_k=1)[0]["audio tags"][0][0]
+
+
+def test_label_assets(capsys):
+    whisper_at.print_label_name("en")
+    out = capsys.readouterr().out.splitlines()
+    assert len(out) == 527 and out[0] == "index: 0 : Speech"
+    whisper_at.print_support_language()
+    out = capsys.readouterr().out.splitlines()
+    assert len(out) == 85 and out[0] == "language code: en : english"
+
+
+def test_synth_is_deterministic():
+    a, b = synth.synth_clip(3), synth.synth_clip(3)
+    assert torch.equal(a, b) and a.shape == (480000,) and a.dtype == torch.float32
+    assert synth.synth_clip(7)[-160000:].abs().max() == 0
+    s1 = synth.synth_state_dict(80, 384, 4, False, seed=1, init="lively")
+    s2 = synth.synth_state_dict(80, 384, 4, False, seed=1, init="lively")
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
+    assert not torch.equal(s1["encoder.conv1.weight"], synth.synth_state_dict(80, 384, 4, False, seed=2, init="lively")["encoder.conv1.weight"])

@@ -1,0 +1,251 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands fed by TMA).
+//
+//   C[M, N] = epilogue( A[M, K] . W[N, K]^T )        A, W bf16 row-major (K contiguous)
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer    : A tile 128x64 + W tile BNx64 per stage, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1      MMA issuer      : one thread issues 4 x tcgen05.mma (M128, N=BN, K16) per stage; tcgen05.commit
+//                                 releases the smem stage / publishes the accumulator
+//   warps 2..5  epilogue        : tcgen05.ld (lane = output row), bias / GELU / residual / layout, global stores
+// Two accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Tiles are ordered n-fastest so the CTAs that share an A row-block run together and A is read from HBM once.
+//
+// Used for every dense contraction of the path (reference call sites: model.py:36 F.linear via Linear,
+// model.py:47 conv via im2col): QKV, attention out-proj, MLP fc1/fc2, conv stem, TL-TR head linears.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wat {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;                       // 512 or 256: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmTcDev {
+  const float* bias;
+  void* C; long long ldc;
+  const float* R; long long ldr; int r_mod;
+  int M, N, K, act, epi;
+  __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (g.M + TC_BM - 1) / TC_BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = (g.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(sa);
+          const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);   // +32 B per K=16 step
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * TC_BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      int vb = 0, vtok = 0;
+      if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tc_wait_ld();
+        if (c0 + 32 == BN) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); }
+        const int n0 = n_blk * BN + c0;
+        if (!row_ok || n0 >= g.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (g.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (g.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
+                                 pack_bf16(v[i + 6], v[i + 7]));
+            *reinterpret_cast<uint4*>(cp + i) = u;
+          }
+        } else if (g.epi == TC_EPI_QKV) {
+          const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
+          const int h = vc >> 6, e0 = vc & 63;
+          __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * 64 + e0) * g.seq_Tpad + vtok;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vp[(long long)i * g.seq_Tpad] = __float2bfloat16_rn(v[i]);
+        } else {
+          if (g.epi == TC_EPI_F32_RES) {
+            const long long rr = g.r_mod > 0 ? (row % g.r_mod) : row;
+            const float* rp = g.R + rr * g.ldr + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+              v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+            }
+          }
+          float* cp = reinterpret_cast<float*>(g.C) + (long long)row * g.ldc + n0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row stride ld (elements); box = 64 cols x box_rows, 128B swizzle
+static bool make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
+  if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, BN)) return cudaErrorInvalidValue;
+  GemmTcDev d;
+  d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
+  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  const int m_tiles = (g.M + TC_BM - 1) / TC_BM, n_tiles = (g.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
+  if (g.M <= 0) return cudaSuccess;
+  if ((g.K & 7) || (g.lda & 7) || (g.N & 31) || (g.ldc & 7)) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
+  if (g.epi == TC_EPI_QKV && ((g.N % 3) || ((g.N / 3) & 63) || g.seq_T <= 0)) return cudaErrorInvalidValue;
+  if (g.N % 256 == 0) return launch_tc<256>(g, num_sms, st);
+  if (g.N % 128 == 0) return launch_tc<128>(g, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace wat

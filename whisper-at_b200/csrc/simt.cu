@@ -1,0 +1,396 @@
+// fp32 SIMT kernels: the fp32 correctness mode of the encoder/head GEMMs and attention, plus the
+// memory-bound glue every mode uses (LayerNorm, pooling, TL-TR window regroup, short-sequence attention).
+// References: package/whisper-at/whisper_at/model.py:29-31 (LayerNorm fp32), :92-107 (attention),
+// :171-174 (20x average pooling), :351-379 (ATModel.forward).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wat {
+
+// ------------------------------------------------------------------------------------------ fp32 GEMM
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 g) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Ws[SG_BK][SG_BN + 4];
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const float* A = g.A;
+  const int tid = threadIdx.x;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += SG_BK) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), wv = av;
+    if (m0 + lr < g.M && k0 + lk < g.K) av = *reinterpret_cast<const float4*>(A + (long long)(m0 + lr) * g.lda + k0 + lk);
+    if (n0 + lr < g.N && k0 + lk < g.K) wv = *reinterpret_cast<const float4*>(g.W + (long long)(n0 + lr) * g.K + k0 + lk);
+    __syncthreads();
+    As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+    Ws[lk + 0][lr] = wv.x; Ws[lk + 1][lr] = wv.y; Ws[lk + 2][lr] = wv.z; Ws[lk + 3][lr] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      if (g.act == 1) v = gelu_erf(v);
+      if (g.R) v += g.R[(long long)(g.r_mod > 0 ? m % g.r_mod : m) * g.ldr + n];
+      g.C[(long long)m * g.ldc + n] = v;
+    }
+  }
+}
+
+cudaError_t launch_gemm_f32(const GemmF32& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  if ((g.K & 3) || (g.lda & 3)) return cudaErrorInvalidValue;
+  dim3 grid((g.N + SG_BN - 1) / SG_BN, (g.M + SG_BM - 1) / SG_BM, 1);
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(g);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  uint2 u = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int M, int D, OutT* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)row * D;
+  float s = 0.f;
+  for (int e = lane * 4; e < D; e += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + e);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int e = lane * 4; e < D; e += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + e);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+  OutT* o = out + (long long)row * D;
+  for (int e = lane * 4; e < D; e += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + e);
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + e);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + e);
+    float4 y;
+    y.x = (v.x - mean) * rstd * gm.x + bt.x;
+    y.y = (v.y - mean) * rstd * gm.y + bt.y;
+    y.z = (v.z - mean) * rstd * gm.z + bt.z;
+    y.w = (v.w - mean) * rstd * gm.w + bt.w;
+    store4<OutT>(o + e, y);
+  }
+}
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int D, void* out,
+                             bool out_bf16, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  if (D & 3) return cudaErrorInvalidValue;
+  const int grid = (M + 7) / 8;
+  if (out_bf16) layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (__nv_bfloat16*)out);
+  else layernorm_kernel<float><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (float*)out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ fp32 attention, hd 64
+constexpr int AF_KT = 32;
+
+__global__ void __launch_bounds__(128) attn_f32_hd64_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                            const float* __restrict__ v, long long ld,
+                                                            float* __restrict__ out, long long ldo, int T, float c_log2) {
+  __shared__ __align__(16) float Ks[AF_KT][64];
+  __shared__ __align__(16) float Vs[AF_KT][64];
+  const int h = blockIdx.y;
+  const long long base = (long long)blockIdx.z * T;
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x * 128 + tid;
+  const bool valid = t < T;
+  float qr[64], o[64];
+#pragma unroll
+  for (int e = 0; e < 64; e += 4) {
+    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v4 = *reinterpret_cast<const float4*>(q + (base + t) * ld + h * 64 + e);
+    qr[e] = v4.x * c_log2; qr[e + 1] = v4.y * c_log2; qr[e + 2] = v4.z * c_log2; qr[e + 3] = v4.w * c_log2;
+    o[e] = o[e + 1] = o[e + 2] = o[e + 3] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int kt0 = 0; kt0 < T; kt0 += AF_KT) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128;
+      const int r = idx >> 4, c4 = (idx & 15) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (kt0 + r < T) {
+        kv = *reinterpret_cast<const float4*>(k + (base + kt0 + r) * ld + h * 64 + c4);
+        vv = *reinterpret_cast<const float4*>(v + (base + kt0 + r) * ld + h * 64 + c4);
+      }
+      *reinterpret_cast<float4*>(&Ks[r][c4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[r][c4]) = vv;
+    }
+    __syncthreads();
+    float s[AF_KT];
+    float mt = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AF_KT; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 64; e += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j][e]);
+        a = fmaf(qr[e], k4.x, a); a = fmaf(qr[e + 1], k4.y, a); a = fmaf(qr[e + 2], k4.z, a); a = fmaf(qr[e + 3], k4.w, a);
+      }
+      s[j] = (kt0 + j < T) ? a : -INFINITY;
+      mt = fmaxf(mt, s[j]);
+    }
+    const float m_new = fmaxf(m, mt);
+    const float alpha = exp2f(m - m_new);
+    l *= alpha;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) o[e] *= alpha;
+#pragma unroll
+    for (int j = 0; j < AF_KT; ++j) {
+      const float p = exp2f(s[j] - m_new);
+      l += p;
+#pragma unroll
+      for (int e = 0; e < 64; e += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j][e]);
+        o[e] = fmaf(p, v4.x, o[e]); o[e + 1] = fmaf(p, v4.y, o[e + 1]);
+        o[e + 2] = fmaf(p, v4.z, o[e + 2]); o[e + 3] = fmaf(p, v4.w, o[e + 3]);
+      }
+    }
+    m = m_new;
+  }
+  if (valid) {
+    const float inv = 1.0f / l;
+    float* op = out + (base + t) * ldo + h * 64;
+#pragma unroll
+    for (int e = 0; e < 64; e += 4)
+      *reinterpret_cast<float4*>(op + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+  }
+}
+
+cudaError_t launch_attn_f32_hd64(const float* q, const float* k, const float* v, long long ld, float* out,
+                                 long long ldo, int n_seq, int T, int n_head, cudaStream_t st) {
+  dim3 grid((T + 127) / 128, n_head, n_seq);
+  const float c = 0.125f * 1.4426950408889634f;            // (64^-0.25)^2 * log2(e)
+  attn_f32_hd64_kernel<<<grid, 128, 0, st>>>(q, k, v, ld, out, ldo, T, c);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ short-sequence attention
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) attn_small_kernel(const TIn* __restrict__ qkv, TOut* __restrict__ out, int T,
+                                                         int n_head, int hd, float scale2) {
+  extern __shared__ float S[];                            // [T][T+1]
+  const int seq = blockIdx.x, h = blockIdx.y;
+  const int D = n_head * hd;
+  const long long row0 = (long long)seq * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ldS = T + 1;
+  for (int p = warp; p < T * T; p += 8) {
+    const int i = p / T, j = p - i * T;
+    const TIn* qp = qkv + (row0 + i) * 3 * D + h * hd;
+    const TIn* kp = qkv + (row0 + j) * 3 * D + D + h * hd;
+    float a = 0.f;
+    for (int e = lane * 4; e < hd; e += 128) {
+      const float4 q4 = load4(qp + e), k4 = load4(kp + e);
+      a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) S[i * ldS + j] = a * scale2;
+  }
+  __syncthreads();
+  for (int i = warp; i < T; i += 8) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, S[i * ldS + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float p = expf(S[i * ldS + j] - mx);
+      S[i * ldS + j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < T; j += 32) S[i * ldS + j] *= inv;
+  }
+  __syncthreads();
+  const int hd4 = hd >> 2;
+  for (int idx = threadIdx.x; idx < T * hd4; idx += 256) {
+    const int i = idx / hd4, e = (idx - i * hd4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < T; ++j) {
+      const float p = S[i * ldS + j];
+      const float4 v4 = load4(qkv + (row0 + j) * 3 * D + 2 * D + h * hd + e);
+      acc.x = fmaf(p, v4.x, acc.x); acc.y = fmaf(p, v4.y, acc.y); acc.z = fmaf(p, v4.z, acc.z); acc.w = fmaf(p, v4.w, acc.w);
+    }
+    store4<TOut>(out + (row0 + i) * D + h * hd + e, acc);
+  }
+}
+
+cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out_bf16, int n_seq, int T, int n_head,
+                              int hd, cudaStream_t st) {
+  if (n_seq <= 0) return cudaSuccess;
+  if (T > 128 || (hd & 3)) return cudaErrorInvalidValue;
+  dim3 grid(n_seq, n_head);
+  const size_t smem = sizeof(float) * T * (T + 1);
+  const float scale2 = 1.0f / sqrtf((float)hd);           // (hd^-0.25)^2
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(attn_small_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+  }
+  if (!in_bf16 && !out_bf16)
+    attn_small_kernel<float, float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, T, n_head, hd, scale2);
+  else if (in_bf16 && out_bf16)
+    attn_small_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ means / pooling / regroup
+__global__ void group_mean_kernel(const float* __restrict__ x, int win, int D, float* __restrict__ out, long long out_stride) {
+  const int g = blockIdx.x;
+  const float inv = 1.0f / (float)win;
+  for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < win; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(x + ((long long)g * win + r) * D + e);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (long long)g * out_stride + e) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+
+cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride, cudaStream_t st) {
+  if (n_groups <= 0) return cudaSuccess;
+  group_mean_kernel<<<n_groups, 128, 0, st>>>(x, win, D, out, out_stride);
+  return cudaGetLastError();
+}
+
+__global__ void pool20_kernel(const float* __restrict__ x, int T, int D, int layer, int L, float* __restrict__ pooled) {
+  const int P = T / 20;
+  const int g = blockIdx.x;                                // b * P + w
+  const int b = g / P, w = g - b * P;
+  const float* src = x + ((long long)b * T + (long long)w * 20) * D;
+  float* dst = pooled + (((long long)b * L + layer) * P + w) * D;
+  for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < 20; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * D + e);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dst + e) = make_float4(a.x * 0.05f, a.y * 0.05f, a.z * 0.05f, a.w * 0.05f);
+  }
+}
+
+cudaError_t launch_pool20(const float* x, int B, int T, int D, int layer, int L, float* pooled, cudaStream_t st) {
+  pool20_kernel<<<B * (T / 20), 128, 0, st>>>(x, T, D, layer, L, pooled);
+  return cudaGetLastError();
+}
+
+__global__ void head_gather_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
+                                   int S, int D, float* __restrict__ out) {
+  // out row = ((b*S + s)*L + l)*dw + tau
+  long long r = blockIdx.x;
+  const int tau = (int)(r % dw); r /= dw;
+  const int l = (int)(r % L); r /= L;
+  const int s = (int)(r % S);
+  const int b = (int)(r / S);
+  const int t = s * dw + tau;
+  float* o = out + (long long)blockIdx.x * D;
+  if (t < Tp) {
+    const float* src = pooled + (((long long)b * L + l) * Tp_total + t_start + t) * D;
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4)
+      *reinterpret_cast<float4*>(o + e) = *reinterpret_cast<const float4*>(src + e);
+  } else {
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
+                               float* out, cudaStream_t st) {
+  const long long rows = (long long)B * S * L * dw;
+  if (rows <= 0) return cudaSuccess;
+  head_gather_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------ im2col (k=3, pad=1)
+__global__ void im2col_k3_kernel(const uint4* __restrict__ src, int Tin, int Cv, int stride, int Tout, uint4* __restrict__ out) {
+  const long long row = blockIdx.x;
+  const int b = (int)(row / Tout), j = (int)(row - (long long)b * Tout);
+  for (int i = threadIdx.x; i < 3 * Cv; i += blockDim.x) {
+    const int k = i / Cv, c = i - k * Cv;
+    const int t = j * stride + k - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < Tin) v = src[((long long)b * Tin + t) * Cv + c];
+    out[row * 3 * Cv + i] = v;
+  }
+}
+
+cudaError_t launch_im2col_k3(const void* src, bool bf16, int B, int Tin, int C, int stride, int Tout, void* out,
+                             cudaStream_t st) {
+  const int per16 = bf16 ? 8 : 4;
+  if (C % per16) return cudaErrorInvalidValue;
+  im2col_k3_kernel<<<(unsigned)((long long)B * Tout), 128, 0, st>>>((const uint4*)src, Tin, C / per16, stride, Tout, (uint4*)out);
+  return cudaGetLastError();
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += step) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 65535) blocks = 65535;
+  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace wat
