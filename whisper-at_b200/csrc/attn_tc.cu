@@ -22,6 +22,80 @@ constexpr int AT_P_BYTES = 128 * 128 * 2;     // 32 KB (two 128x64 K-blocks of 1
 constexpr int AT_SMEM = AT_Q_BYTES + 2 * AT_K_BYTES + AT_V_BYTES + AT_P_BYTES + 1024 + 128;
 constexpr int AT_TMEM_COLS = 256;             // S: cols [0,128), O: cols [128,192)
 
+// One KV tile of the online softmax for one query row (thread == TMEM lane).
+//   pass 1: row max of S (two chunks in flight);  pass 2: P = 2^(S*c - m) -> bf16 into the swizzled smem tile.
+// The reference max m_used is only moved when the true max exceeds it by more than 2^8 (lazy rescale, as in
+// FlashAttention-4): P stays <= 256, the O accumulator in TMEM is rescaled only on those rare steps, and the final
+// O / l is unchanged.  MASK handles the ragged last tile (keys >= nvalid are excluded).
+template <bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
+                                             bool have_o, float& m_used, float& l) {
+  uint32_t a[32], b[32];
+  float mx = -INFINITY;
+  tmem_ld32(tS, a);
+  tmem_ld32(tS + 32, b);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (!MASK || i < nvalid) mx = fmaxf(mx, __uint_as_float(a[i]));
+    if (!MASK || 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(b[i]));
+  }
+  tmem_ld32(tS + 64, a);
+  tmem_ld32(tS + 96, b);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (!MASK || 64 + i < nvalid) mx = fmaxf(mx, __uint_as_float(a[i]));
+    if (!MASK || 96 + i < nvalid) mx = fmaxf(mx, __uint_as_float(b[i]));
+  }
+  mx *= c_log2;
+  const bool need = mx > m_used + 8.0f;
+  if (__any_sync(0xffffffffu, need)) {
+    const float m_new = need ? mx : m_used;
+    const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
+    l *= alpha;
+    m_used = m_new;
+    if (have_o) {
+      tmem_ld32(tO, a);
+      tmem_ld32(tO + 32, b);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        a[i] = __float_as_uint(__uint_as_float(a[i]) * alpha);
+        b[i] = __float_as_uint(__uint_as_float(b[i]) * alpha);
+      }
+      tmem_st32(tO, a);
+      tmem_st32(tO + 32, b);
+      tc_wait_st();
+    }
+  }
+  const float neg_m = -m_used;
+  float lsum = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld32(tS + half * 64, a);
+    tmem_ld32(tS + half * 64 + 32, b);
+    tc_wait_ld();
+    uint8_t* blk = p_row + half * 16384;                          // K-block (64 keys) of the P tile
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+      float p[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = g4 * 8 + e;                                 // column inside this half
+        const float sv = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
+        float pv = ex2_approx(fmaf(sv, c_log2, neg_m));
+        if (MASK && half * 64 + i >= nvalid) pv = 0.f;
+        p[e] = pv;
+        lsum += pv;
+      }
+      *reinterpret_cast<uint4*>(blk + ((g4 ^ sw) << 4)) =
+          make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    }
+  }
+  l += lsum;
+}
+
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
                __nv_bfloat16* __restrict__ out, int T, int D, int n_head, int q_tiles, float c_log2) {
@@ -119,59 +193,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8) and row sum
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int nvalid = min(128, T - j * 128);
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
-      }
-      const float m_new = fmaxf(m, mx * c_log2);
-      const float alpha = exp2f(m - m_new);
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tc_wait_ld();
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          p[i] = (c * 32 + i < nvalid) ? exp2f(fmaf(__uint_as_float(v[i]), c_log2, -m_new)) : 0.f;
-          lsum += p[i];
-        }
-        uint8_t* blk = p_row + (c >> 1) * 16384;
-#pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          const int chunk = (c & 1) * 4 + g4;                     // 16-byte chunk inside the 128-byte row
-          uint4 u = make_uint4(pack_bf16(p[g4 * 8 + 0], p[g4 * 8 + 1]), pack_bf16(p[g4 * 8 + 2], p[g4 * 8 + 3]),
-                               pack_bf16(p[g4 * 8 + 4], p[g4 * 8 + 5]), pack_bf16(p[g4 * 8 + 6], p[g4 * 8 + 7]));
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = u;
-        }
-      }
-      l = l * alpha + lsum;
-      m = m_new;
-      if (j > 0) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_O + lane_off + c * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tmem_O + lane_off + c * 32, v);
-        }
-        tc_wait_st();
-      }
+      const int nvalid = T - j * 128;
+      if (nvalid >= 128) softmax_tile<false>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, 128, j > 0, m_used, l);
+      else softmax_tile<true>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j > 0, m_used, l);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -181,21 +211,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     const int tq = qt * 128 + r;
     const float inv = 1.0f / l;
     __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_O + lane_off + c * 32, v);
-      tc_wait_ld();
-      if (tq < T) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(tmem_O + lane_off, v0);
+    tmem_ld32(tmem_O + lane_off + 32, v1);
+    tc_wait_ld();
+    if (tq < T) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u = make_uint4(pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
-                               pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
-                               pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
-                               pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
-          *reinterpret_cast<uint4*>(op + c * 32 + i) = u;
-        }
-      }
+      for (int i = 0; i < 32; i += 8)
+        *reinterpret_cast<uint4*>(op + i) =
+            make_uint4(pack_bf16(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv),
+                       pack_bf16(__uint_as_float(v0[i + 2]) * inv, __uint_as_float(v0[i + 3]) * inv),
+                       pack_bf16(__uint_as_float(v0[i + 4]) * inv, __uint_as_float(v0[i + 5]) * inv),
+                       pack_bf16(__uint_as_float(v0[i + 6]) * inv, __uint_as_float(v0[i + 7]) * inv));
+#pragma unroll
+      for (int i = 0; i < 32; i += 8)
+        *reinterpret_cast<uint4*>(op + 32 + i) =
+            make_uint4(pack_bf16(__uint_as_float(v1[i]) * inv, __uint_as_float(v1[i + 1]) * inv),
+                       pack_bf16(__uint_as_float(v1[i + 2]) * inv, __uint_as_float(v1[i + 3]) * inv),
+                       pack_bf16(__uint_as_float(v1[i + 4]) * inv, __uint_as_float(v1[i + 5]) * inv),
+                       pack_bf16(__uint_as_float(v1[i + 6]) * inv, __uint_as_float(v1[i + 7]) * inv));
     }
   }
 

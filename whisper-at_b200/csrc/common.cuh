@@ -10,11 +10,10 @@
 namespace wat {
 
 // ------------------------------------------------------------------------------------------
-// watchdog: every mbarrier wait is bounded so a protocol bug traps instead of hanging the GPU
-// (a hung box is a strike on the shared pool).  ~2^26 polls of a HW-sleeping try_wait >> any
-// legitimate wait in these kernels.
-#ifndef WAT_WATCHDOG_POLLS
-#define WAT_WATCHDOG_POLLS (1u << 26)
+// watchdog: every mbarrier wait is bounded (wall time, %globaltimer) so a protocol bug traps instead of
+// hanging the GPU (a hung box is a strike on the shared pool).
+#ifndef WAT_WATCHDOG_NS
+#define WAT_WATCHDOG_NS 4000000000ull
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -46,25 +45,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of polling, so a waiting producer / MMA thread does not steal issue slots from the math warps
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t polls = 0;
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > WAT_WATCHDOG_POLLS) {
+    if (global_timer_ns() - t0 > WAT_WATCHDOG_NS) {
       printf("wat: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ------------------------------------------------------------------------------------------ TMA
@@ -163,6 +172,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 // ------------------------------------------------------------------------------------------ math
+__device__ __forceinline__ float ex2_approx(float x) {           // single MUFU.EX2 (flush-to-zero, no range fix-up)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
