@@ -135,7 +135,7 @@ def _dbg_gemm(A, W, bias, R, act, tc):
 
 @pytest.mark.parametrize("M,N,K,act,res", [(128, 256, 64, 0, False), (300, 384, 240, 1, False), (1500, 1280, 1280, 0, True),
                                            (4097, 512, 2048, 1, True), (77, 128, 384, 0, False)])
-@pytest.mark.parametrize("tc", [0, 1], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("tc", [0, 1, 2], ids=["simt", "tcgen05", "ctapair"])
 def test_gemm_kernels_vs_torch(tc, M, N, K, act, res):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).cuda()

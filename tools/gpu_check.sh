@@ -12,6 +12,7 @@ print('tma overlap probe:', _lib.lib().wat_dbg_tma_overlap_probe())
 run mel -k "mel"
 run gemm_f32 -k "gemm_kernels and simt"
 run gemm_tc -k "gemm_kernels and tcgen05"
+run gemm_pair -k "gemm_kernels and ctapair"
 run attn_f32 -k "attention_kernels and simt"
 run attn_tc -k "attention_kernels and tcgen05"
 run fp32_model -k "fp32_vs_reference or encoder_x_output or transcribe"

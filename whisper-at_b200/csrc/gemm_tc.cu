@@ -6,12 +6,15 @@
 //   warp 0      TMA producer    : A tile 128x64 + W tile BNx64 per stage, SWIZZLE_128B, mbarrier complete_tx
 //   warp 1      MMA issuer      : one thread issues 4 x tcgen05.mma (M128, N=BN, K16) per stage; tcgen05.commit
 //                                 releases the smem stage / publishes the accumulator
-//   warps 2..5  epilogue        : tcgen05.ld (lane = output row), bias / GELU / residual / layout, global stores
+//   warps 2..9  epilogue        : tcgen05.ld (lane = output row; two warps per TMEM lane quadrant, each half of
+//                                 the columns), bias / GELU / residual / layout, global stores
 // Two accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // Tiles are ordered n-fastest so the CTAs that share an A row-block run together and A is read from HBM once.
 //
 // Used for every dense contraction of the path (reference call sites: model.py:36 F.linear via Linear,
 // model.py:47 conv via im2col): QKV, attention out-proj, MLP fc1/fc2, conv stem, TL-TR head linears.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,7 +22,7 @@ namespace wat {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                 // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 
 template <int BN>
@@ -38,6 +41,53 @@ struct GemmTcDev {
   int M, N, K, act, epi;
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
 };
+
+// bias / activation / residual / layout for 32 consecutive columns [n0, n0+32) of output row `row`
+__device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok) {
+  if (!row_ok || n0 >= g.N) return;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (g.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+      v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+    }
+  }
+  if (g.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 u = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
+                           pack_bf16(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(cp + i) = u;
+    }
+  } else if (g.epi == TC_EPI_QKV) {
+    const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
+    const int h = vc >> 6, e0 = vc & 63;
+    __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * 64 + e0) * g.seq_Tpad + vtok;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) vp[(long long)i * g.seq_Tpad] = __float2bfloat16_rn(v[i]);
+  } else {
+    if (g.epi == TC_EPI_F32_RES) {
+      const long long rr = g.r_mod > 0 ? (row % g.r_mod) : row;
+      const float* rp = g.R + rr * g.ldr + n0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+        v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+      }
+    }
+    float* cp = reinterpret_cast<float*>(g.C) + (long long)row * g.ldc + n0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -65,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 256); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -90,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
@@ -116,8 +167,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&tmem_full[as]);
       }
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;                          // which half of the tile's columns
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
@@ -131,55 +184,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int vb = 0, vtok = 0;
       if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
         tc_wait_ld();
-        if (c0 + 32 == BN) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); }
-        const int n0 = n_blk * BN + c0;
-        if (!row_ok || n0 >= g.N) continue;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (g.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-          }
-        }
-        if (g.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        }
-        if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 u = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
-                                 pack_bf16(v[i + 6], v[i + 7]));
-            *reinterpret_cast<uint4*>(cp + i) = u;
-          }
-        } else if (g.epi == TC_EPI_QKV) {
-          const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
-          const int h = vc >> 6, e0 = vc & 63;
-          __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * 64 + e0) * g.seq_Tpad + vtok;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) vp[(long long)i * g.seq_Tpad] = __float2bfloat16_rn(v[i]);
-        } else {
-          if (g.epi == TC_EPI_F32_RES) {
-            const long long rr = g.r_mod > 0 ? (row % g.r_mod) : row;
-            const float* rp = g.R + rr * g.ldr + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-              v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
-            }
-          }
-          float* cp = reinterpret_cast<float*>(g.C) + (long long)row * g.ldc + n0;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
+        if (c0 + 32 == (chalf + 1) * (BN / 2)) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); }
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok);
       }
     }
   }
@@ -187,6 +197,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+
+// ------------------------------------------------------------------------------------------ CTA-pair variant
+// 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2, MMA M = 256): each CTA stages its own 128 A
+// rows and HALF of the W tile (128 of the 256 N rows), so a k-block costs 32 KB of L2->smem traffic per SM instead
+// of 48 KB for the same 128x256x64 MACs per SM; 6 pipeline stages fit instead of 4.  The leader CTA (rank 0) owns the
+// `full` barriers (both CTAs' TMA bytes are signalled there) and issues every MMA; tcgen05.commit multicasts the
+// stage-free / accumulator-ready arrivals to both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes.
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_STAGE_BYTES = 2 * TC_A_BYTES;                  // A 128x64 + W-half 128x64
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + TC2_STAGES;
+  uint64_t* tmem_full = bars + 2 * TC2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  const int m_pairs = (g.M + 2 * TC_BM - 1) / (2 * TC_BM);
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total_tiles = m_pairs * n_tiles;
+  const int k_blocks = (g.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }   // 8 warps x 2 CTAs
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
+        const int row0 = m_pair * 2 * TC_BM + (int)rank * TC_BM;
+        const int col0 = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);
+          const uint32_t bar_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(sa, &tmA, bar_leader, kb * TC_BK, row0);
+          tma_load_2d_pair(sb, &tmB, bar_leader, kb * TC_BK, col0);
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC2_STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(sa);
+          const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[as], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      int vb = 0, vtok = 0;
+      if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
+#pragma unroll 1
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tc_wait_ld();
+        if (c0 + 32 == (chalf + 1) * (BN / 2)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+        }
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -238,11 +378,44 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
+  if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, 128)) return cudaErrorInvalidValue;      // each CTA loads half of the 256 W rows
+  GemmTcDev d;
+  d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
+  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
+  int clusters = num_sms / 2;
+  if (clusters > total) clusters = total;
+  gemm_tc2_kernel<<<2 * clusters, TC_THREADS, TC2_SMEM_BYTES, st>>>(tmA, tmB, d);
+  return cudaGetLastError();
+}
+
+// 0: 1-CTA kernel, 1: CTA-pair kernel when the shape allows (N % 256 == 0).  WAT_GEMM_PAIR=0/1 overrides.
+static int pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("WAT_GEMM_PAIR");
+    mode = e ? (atoi(e) != 0) : 1;
+  }
+  return mode;
+}
+
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   if (g.M <= 0) return cudaSuccess;
   if ((g.K & 7) || (g.lda & 7) || (g.N & 31) || (g.ldc & 7)) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
   if (g.epi == TC_EPI_QKV && ((g.N % 3) || ((g.N / 3) & 63) || g.seq_T <= 0)) return cudaErrorInvalidValue;
+  if (g.N % 256 == 0 && (g.force_pair > 0 || (g.force_pair == 0 && pair_mode() && g.M >= 256))) return launch_tc2(g, num_sms, st);
   if (g.N % 256 == 0) return launch_tc<256>(g, num_sms, st);
   if (g.N % 128 == 0) return launch_tc<128>(g, num_sms, st);
   return cudaErrorInvalidValue;

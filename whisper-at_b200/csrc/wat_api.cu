@@ -713,6 +713,7 @@ int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float*
   memset(&g, 0, sizeof(g));
   g.A = Ah; g.lda = K; g.W = Wh; g.bias = bias; g.C = C; g.ldc = N; g.R = R; g.ldr = N; g.r_mod = 0;
   g.M = M; g.N = N; g.K = K; g.act = act; g.epi = R ? TC_EPI_F32_RES : TC_EPI_F32;
+  g.force_pair = tc == 2 ? 1 : -1;                               // tc: 1 = single-CTA kernel, 2 = CTA-pair kernel
   cudaError_t e = launch_gemm_tc(g, sms, st);
   cudaError_t e2 = cudaStreamSynchronize(st);
   cudaFree(Ah); cudaFree(Wh);
