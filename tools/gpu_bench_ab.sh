@@ -2,7 +2,7 @@
 # A/B: CTA-pair GEMM on/off, default workload, no profiler
 mkdir -p gpurun_out
 export PYTHONDONTWRITEBYTECODE=1
-for pair in 1 0; do
+for pair in ${PAIRS:-1}; do
   WAT_GEMM_PAIR=$pair timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pair$pair.json 2> gpurun_out/bench_pair$pair.err
   echo "pair=$pair exit $?"; python - <<PY
 import json

@@ -29,7 +29,7 @@ constexpr int AT_TMEM_COLS = 256;             // S: cols [0,128), O: cols [128,1
 // O / l is unchanged.  MASK handles the ragged last tile (keys >= nvalid are excluded).
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
-                                             bool have_o, float& m_used, float& l) {
+                                             uint64_t* prev_pv, uint32_t prev_par, float& m_used, float& l) {
   uint32_t a[32], b[32];
   float mx = -INFINITY;
   tmem_ld32(tS, a);
@@ -49,6 +49,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
     if (!MASK || 96 + i < nvalid) mx = fmaxf(mx, __uint_as_float(b[i]));
   }
   mx *= c_log2;
+  // PV(j-1) must have finished before O is rescaled or the P tile is overwritten (it ran under the max pass above)
+  const bool have_o = prev_pv != nullptr;
+  if (have_o) { mbar_wait_spin(prev_pv, prev_par); tc_fence_after(); }
   const bool need = mx > m_used + 8.0f;
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? mx : m_used;
@@ -114,7 +117,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
   uint64_t* v_empty = bars + 6;     // 1
   uint64_t* s_full = bars + 7;      // 1
   uint64_t* p_full = bars + 8;      // 1 (128 arrivals)
-  uint64_t* o_full = bars + 9;      // 1
+  uint64_t* pv_done = bars + 9;     // 1: PV(j) finished (O and the P tile may be touched again); the last one = O final
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,7 +133,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
     mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
@@ -166,17 +169,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
       const uint64_t dP = make_smem_desc_sw128(smem_u32(sP));
       const uint64_t dV = make_smem_desc_sw128(smem_u32(sV));
       mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ks = j & 1;
-        const uint32_t kph = (j >> 1) & 1;
-        mbar_wait(&k_full[ks], kph);
-        tc_fence_after();
-        const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + ks * AT_K_BYTES));
+      // S(0) = Q K(0)^T
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, dQ + 2 * k, dK + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
-        umma_commit(&k_empty[ks]);
-        mbar_wait(p_full, j & 1);
+        umma_commit(&k_empty[0]);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait_spin(p_full, j & 1);                            // softmax(j) has consumed S(j) and written P(j)
+        tc_fence_after();
+        if (j + 1 < n_kv) {                                       // S(j+1) first: the next softmax starts while PV(j) runs
+          const int ks = (j + 1) & 1;
+          mbar_wait(&k_full[ks], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + ks * AT_K_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, dQ + 2 * k, dK + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+          umma_commit(&k_empty[ks]);
+        }
         mbar_wait(v_full, j & 1);
         tc_fence_after();
 #pragma unroll
@@ -185,8 +200,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
           umma_bf16_ss(tmem_O, dP + kb * (16384 >> 4) + 2 * kk, dV + kb * (8192 >> 4) + 2 * kk, idesc_o, (j | k) != 0);
         }
         umma_commit(v_empty);
+        umma_commit(pv_done);
       }
-      umma_commit(o_full);
     }
     __syncwarp();
   } else {
@@ -197,16 +212,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     uint8_t* p_row = sP + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait_spin(s_full, j & 1);
       tc_fence_after();
       const int nvalid = T - j * 128;
-      if (nvalid >= 128) softmax_tile<false>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, 128, j > 0, m_used, l);
-      else softmax_tile<true>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j > 0, m_used, l);
+      uint64_t* prev_pv = j > 0 ? pv_done : nullptr;
+      const uint32_t prev_par = (j - 1) & 1;
+      if (nvalid >= 128) softmax_tile<false>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, 128, prev_pv, prev_par, m_used, l);
+      else softmax_tile<true>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, nvalid, prev_pv, prev_par, m_used, l);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    mbar_wait(o_full, 0);
+    mbar_wait_spin(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const int tq = qt * 128 + r;
     const float inv = 1.0f / l;

@@ -43,8 +43,49 @@ struct GemmTcDev {
 };
 
 // bias / activation / residual / layout for 32 consecutive columns [n0, n0+32) of output row `row`
-__device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok) {
-  if (!row_ok || n0 >= g.N) return;
+// `stage` (optional, warp-private 32 x 36 floats): fp32 outputs are transposed through it so that global accesses are
+// 128-byte coalesced (8 lanes x 16 B per row) instead of one 16 B access per row.
+__device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok,
+                                                  float* stage = nullptr, int lane = 0) {
+  if (n0 >= g.N) return;
+  if (stage != nullptr && (g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32)) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (g.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+      }
+    }
+    if (g.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    __syncwarp();
+    const int row_base = row - lane;
+    const int cc = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int grow = row_base + rr;
+      if (grow < g.M) {
+        float4 t = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
+        if (g.epi == TC_EPI_F32_RES) {
+          const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
+          const float4 r4 = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+          t.x += r4.x; t.y += r4.y; t.z += r4.z; t.w += r4.w;
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t;
+      }
+    }
+    __syncwarp();
+    return;
+  }
+  if (!row_ok) return;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -57,7 +98,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
   }
   if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
@@ -203,12 +244,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------ CTA-pair variant
 // 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2, MMA M = 256): each CTA stages its own 128 A
 // rows and HALF of the W tile (128 of the 256 N rows), so a k-block costs 32 KB of L2->smem traffic per SM instead
-// of 48 KB for the same 128x256x64 MACs per SM; 6 pipeline stages fit instead of 4.  The leader CTA (rank 0) owns the
+// of 48 KB for the same 128x256x64 MACs per SM; 5 pipeline stages + the epilogue staging fit.  The leader CTA (rank 0) owns the
 // `full` barriers (both CTAs' TMA bytes are signalled there) and issues every MMA; tcgen05.commit multicasts the
 // stage-free / accumulator-ready arrivals to both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes.
-constexpr int TC2_STAGES = 6;
+constexpr int TC2_STAGES = 5;
 constexpr int TC2_STAGE_BYTES = 2 * TC_A_BYTES;                  // A 128x64 + W-half 128x64
-constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256;
+constexpr int TC2_EPI_STAGE_BYTES = 8 * 32 * 36 * 4;           // 8 epilogue warps x (32 x 36) floats
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + TC2_EPI_STAGE_BYTES;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
@@ -222,6 +264,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * TC2_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -319,7 +362,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
         }
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok);
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, epi_stage + (warp - 2) * (32 * 36), lane);
       }
     }
   }
