@@ -68,19 +68,27 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     __syncwarp();
     const int row_base = row - lane;
     const int cc = (lane & 7) * 4;
+    // all residual loads first (R aliases C for the in-place residual stream, so the compiler would otherwise
+    // serialise load -> add -> store per row and expose one memory latency per iteration)
+    float4 res[8];
+    if (g.epi == TC_EPI_F32_RES) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row_base + it * 4 + (lane >> 3);
+        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < g.M) {
+          const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
+          res[it] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+        }
+      }
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + (lane >> 3);
       const int grow = row_base + rr;
-      if (grow < g.M) {
-        float4 t = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
-        if (g.epi == TC_EPI_F32_RES) {
-          const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
-          const float4 r4 = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
-          t.x += r4.x; t.y += r4.y; t.z += r4.z; t.w += r4.w;
-        }
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t;
-      }
+      float4 t = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
+      if (g.epi == TC_EPI_F32_RES) { t.x += res[it].x; t.y += res[it].y; t.z += res[it].z; t.w += res[it].w; }
+      if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t;
     }
     __syncwarp();
     return;
