@@ -238,7 +238,8 @@ def main():
         pk = peaks()
         prof = {Lb.wat_profile_class_name(i).decode(): dict(ms_per_step=pms[i] / args.steps, launches_per_step=pcnt[i] / args.steps)
                 for i in range(n_cls)}
-        gemm_ms = pms[2] / args.steps
+        gemm_ids = [i for i in range(n_cls) if Lb.wat_profile_class_name(i).decode().startswith('gemm')]
+        gemm_ms = sum(pms[i] for i in gemm_ids) / args.steps
         achieved = fl["gemm"] * B / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         attn_ms = prof["attention"]["ms_per_step"]
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
@@ -254,6 +255,10 @@ def main():
                                  attention_tflops=(fl["attn"] * B / (attn_ms / 1000.0) / 1e12) if attn_ms > 0 else None,
                                  whole_step_tflops=fl["total"] * B / (ms / args.steps / 1000.0) / 1e12),
                    kernel_profile=prof)
+        T = 1500
+        per_kind = {"gemm_qkv": 2 * T * 3 * d * d, "gemm_out": 2 * T * d * d, "gemm_fc1": 2 * T * 4 * d * d, "gemm_fc2": 2 * T * 4 * d * d}
+        out["roofline"]["encoder_gemm_tflops"] = {k: (f * L * B / (prof[k]["ms_per_step"] / 1000.0) / 1e12) if prof[k]["ms_per_step"] > 0 else None
+                                                  for k, f in per_kind.items()}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             tt = oracle_time_clips(args.model, n_mels, args.low, args.res, 1, threads)

@@ -8,7 +8,7 @@ for pair in ${PAIRS:-1}; do
 import json
 try:
     j=json.loads(open('gpurun_out/bench_pair$pair.json').read().strip().splitlines()[-1])
-    print('value',round(j['value']),'e2e',round(j['e2e']['value']),'ms/step',round(j['ms_per_step'],1),'gemm TF',round(j['roofline']['achieved']),'attn TF',round(j['roofline']['attention_tflops']), {k:round(v['ms_per_step'],1) for k,v in j['kernel_profile'].items()}, j['clocks'])
+    print('value',round(j['value']),'e2e',round(j['e2e']['value']),'ms/step',round(j['ms_per_step'],1),'gemm TF',round(j['roofline']['achieved']),'attn TF',round(j['roofline']['attention_tflops']), {k:round(v['ms_per_step'],1) for k,v in j['kernel_profile'].items()}, j['clocks'], {k:round(v) for k,v in j['roofline'].get('encoder_gemm_tflops',{}).items()})
 except Exception as e: print('parse fail',e)
 PY
   tail -3 gpurun_out/bench_pair$pair.err

@@ -2,205 +2,213 @@
 // Reference semantics: model.py:92-107 — softmax((q*s)(k*s)^T) v with s = 64^-0.25, softmax in fp32; the
 // [B, H, T, T] score tensor the reference materialises is never written here.
 //
-// One CTA per (clip, head, 128-query tile); two CTAs are resident per SM (256 TMEM columns, 96 KB smem each) so
-// one CTA's softmax overlaps the other's MMAs.
-//   warp 0      TMA producer : Q tile once; K tile [128 keys x 64] double-buffered; V^T tile [64 x 128 keys]
-//   warp 1      MMA issuer   : S = Q K^T (M128 N128 K64) into TMEM; O += P V (M128 N64 K128), P from smem
-//   warps 2..5  softmax      : thread = query row = TMEM lane: online softmax on S (exp2, fp32), P -> bf16 into the
-//                              128B-swizzled smem tile the MMA reads, O rescale in TMEM, final O / l -> bf16
-// K tail: 1500 = 11*128 + 92; TMA zero-fills rows >= T and those keys are masked to -inf before the softmax.
+// One CTA per (clip, head, 128-query tile), KV tiles of 64 keys; two CTAs are resident per SM (256 TMEM columns,
+// 96 KB smem each).  The exponentials (MUFU.EX2) are the binding resource of this kernel, so everything else is
+// arranged so that the 4 softmax warps never wait:
+//   warp 0      TMA producer : Q tile once; K tiles [64 keys x 64] and V^T tiles [64 x 64 keys], 3 stages each
+//   warp 1      MMA issuer   : S(j+1) = Q K(j+1)^T (M128 N64 K64) into the OTHER of two S buffers in TMEM before it
+//                              waits for P(j); then O += P(j) V(j) (M128 N64 K64) with P(j) read from smem
+//   warps 2..5  softmax      : thread = query row = TMEM lane.  One tcgen05.ld of the 64 scores (kept in registers),
+//                              row max, P = 2^(S*c - m) with one ex2.approx per element, bf16 P into one of two
+//                              128B-swizzled smem tiles, lazy rescale of O in TMEM, final O / l -> bf16
+// K tail: 1500 = 23*64 + 28; TMA zero-fills rows >= T and those keys are excluded in the last tile only.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace wat {
 
 constexpr int AT_THREADS = 192;
+constexpr int AT_KV = 64;                     // keys per step
+constexpr int AT_NSTAGE = 3;                  // K / V^T pipeline stages
 constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
-constexpr int AT_K_BYTES = 128 * 64 * 2;      // 16 KB per stage, 2 stages
-constexpr int AT_V_BYTES = 64 * 128 * 2;      // 16 KB (two 64x64 K-blocks of 8 KB)
-constexpr int AT_P_BYTES = 128 * 128 * 2;     // 32 KB (two 128x64 K-blocks of 16 KB)
-constexpr int AT_SMEM = AT_Q_BYTES + 2 * AT_K_BYTES + AT_V_BYTES + AT_P_BYTES + 1024 + 128;
-constexpr int AT_TMEM_COLS = 256;             // S: cols [0,128), O: cols [128,192)
+constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
+constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
+constexpr int AT_P_BYTES = 128 * AT_KV * 2;   // 16 KB per buffer, 2 buffers
+constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 2 * AT_P_BYTES + 1024 + 256;
+constexpr int AT_TMEM_COLS = 256;             // S0: [0,64)  S1: [64,128)  O: [128,192)
 
-// One KV tile of the online softmax for one query row (thread == TMEM lane).
-//   pass 1: row max of S (two chunks in flight);  pass 2: P = 2^(S*c - m) -> bf16 into the swizzled smem tile.
-// The reference max m_used is only moved when the true max exceeds it by more than 2^8 (lazy rescale, as in
-// FlashAttention-4): P stays <= 256, the O accumulator in TMEM is rescaled only on those rare steps, and the final
-// O / l is unchanged.  MASK handles the ragged last tile (keys >= nvalid are excluded).
+struct AttnBars {
+  uint64_t q_full;
+  uint64_t k_full[AT_NSTAGE], k_empty[AT_NSTAGE];
+  uint64_t v_full[AT_NSTAGE], v_empty[AT_NSTAGE];
+  uint64_t s_full[2];       // S buffer written by the MMA
+  uint64_t p_full[2];       // P buffer written by the 128 softmax threads (and S buffer fully read)
+  uint64_t pv_done[2];      // PV(j) finished: P buffer j&1 reusable, O stable
+  uint32_t tmem_slot;
+};
+
+// One KV tile of the online softmax for one query row (thread == TMEM lane).  The reference max m_used is only moved
+// when the true max exceeds it by more than 2^8 (lazy rescale): P stays <= 256, the O accumulator in TMEM is
+// rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
-                                             uint64_t* prev_pv, uint32_t prev_par, float& m_used, float& l) {
+                                             int j, AttnBars* bars, float& m_used, float& l) {
   uint32_t a[32], b[32];
-  float mx = -INFINITY;
   tmem_ld32(tS, a);
   tmem_ld32(tS + 32, b);
   tc_wait_ld();
+  // four independent max chains (a single chain of 64 dependent FMNMX costs ~4 cycles each)
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (!MASK || i < nvalid) mx = fmaxf(mx, __uint_as_float(a[i]));
-    if (!MASK || 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(b[i]));
+  for (int i = 0; i < 32; i += 2) {
+    if (!MASK || i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(a[i]));
+    if (!MASK || i + 1 < nvalid) mx1 = fmaxf(mx1, __uint_as_float(a[i + 1]));
+    if (!MASK || 32 + i < nvalid) mx2 = fmaxf(mx2, __uint_as_float(b[i]));
+    if (!MASK || 33 + i < nvalid) mx3 = fmaxf(mx3, __uint_as_float(b[i + 1]));
   }
-  tmem_ld32(tS + 64, a);
-  tmem_ld32(tS + 96, b);
-  tc_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (!MASK || 64 + i < nvalid) mx = fmaxf(mx, __uint_as_float(a[i]));
-    if (!MASK || 96 + i < nvalid) mx = fmaxf(mx, __uint_as_float(b[i]));
-  }
+  float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   mx *= c_log2;
-  // PV(j-1) must have finished before O is rescaled or the P tile is overwritten (it ran under the max pass above)
-  const bool have_o = prev_pv != nullptr;
-  if (have_o) { mbar_wait_spin(prev_pv, prev_par); tc_fence_after(); }
   const bool need = mx > m_used + 8.0f;
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
     l *= alpha;
     m_used = m_new;
-    if (have_o) {
-      tmem_ld32(tO, a);
-      tmem_ld32(tO + 32, b);
+    if (j > 0) {                                                  // O holds PV(0..j-1): wait for PV(j-1), then rescale
+      mbar_wait_spin(&bars->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO, o0);
+      tmem_ld32(tO + 32, o1);
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        a[i] = __float_as_uint(__uint_as_float(a[i]) * alpha);
-        b[i] = __float_as_uint(__uint_as_float(b[i]) * alpha);
+        o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+        o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
       }
-      tmem_st32(tO, a);
-      tmem_st32(tO + 32, b);
+      tmem_st32(tO, o0);
+      tmem_st32(tO + 32, o1);
       tc_wait_st();
     }
   }
+  // The P buffer j&1 was last read by PV(j-2).  No wait is needed: s_full(j), which this thread has observed, was
+  // committed by the MMA thread after it issued PV(j-2), and tcgen05.commit tracks every MMA issued before it.
   const float neg_m = -m_used;
-  float lsum = 0.f;
+  // all 64 exponentials first (in place, back-to-back MUFUs), then eight independent partial sums, then pack/store:
+  // keeps the consumer of each MUFU result far behind its issue so the MUFU pipe is never waited on
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    tmem_ld32(tS + half * 64, a);
-    tmem_ld32(tS + half * 64 + 32, b);
-    tc_wait_ld();
-    uint8_t* blk = p_row + half * 16384;                          // K-block (64 keys) of the P tile
-#pragma unroll
-    for (int g4 = 0; g4 < 8; ++g4) {
-      float p[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = g4 * 8 + e;                                 // column inside this half
-        const float sv = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
-        float pv = ex2_approx(fmaf(sv, c_log2, neg_m));
-        if (MASK && half * 64 + i >= nvalid) pv = 0.f;
-        p[e] = pv;
-        lsum += pv;
-      }
-      *reinterpret_cast<uint4*>(blk + ((g4 ^ sw) << 4)) =
-          make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-    }
+  for (int i = 0; i < 32; ++i) {
+    float pa = ex2_approx(fmaf(__uint_as_float(a[i]), c_log2, neg_m));
+    float pb = ex2_approx(fmaf(__uint_as_float(b[i]), c_log2, neg_m));
+    if (MASK && i >= nvalid) pa = 0.f;
+    if (MASK && 32 + i >= nvalid) pb = 0.f;
+    a[i] = __float_as_uint(pa);
+    b[i] = __float_as_uint(pb);
   }
+  float ls[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ls[e] = 0.f;
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    float p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = g4 * 8 + e;
+      p[e] = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
+      ls[e] += p[e];
+    }
+    *reinterpret_cast<uint4*>(p_row + ((g4 ^ sw) << 4)) =
+        make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+  }
+  const float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
   l += lsum;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
-               __nv_bfloat16* __restrict__ out, int T, int D, int n_head, int q_tiles, float c_log2) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
+               int q_tiles, float c_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
-  uint8_t* sV = sK + 2 * AT_K_BYTES;
-  uint8_t* sP = sV + AT_V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* k_full = bars + 1;      // 2
-  uint64_t* k_empty = bars + 3;     // 2
-  uint64_t* v_full = bars + 5;      // 1
-  uint64_t* v_empty = bars + 6;     // 1
-  uint64_t* s_full = bars + 7;      // 1
-  uint64_t* p_full = bars + 8;      // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 9;     // 1: PV(j) finished (O and the P tile may be touched again); the last one = O final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint8_t* sV = sK + AT_NSTAGE * AT_K_BYTES;
+  uint8_t* sP = sV + AT_NSTAGE * AT_V_BYTES;
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 2 * AT_P_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % q_tiles;
   const int bh = blockIdx.x / q_tiles;
   const int h = bh % n_head, b = bh / n_head;
-  const int n_kv = (T + 127) / 128;
+  const int n_kv = (T + AT_KV - 1) / AT_KV;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmVT);
-    mbar_init(q_full, 1);
-    mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
-    mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
-    mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < AT_NSTAGE; ++s) {
+      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); mbar_init(&bars->pv_done[s], 1); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_3d(sQ, &tmQK, q_full, h * 64, qt * 128, b);
+      mbar_expect_tx(&bars->q_full, AT_Q_BYTES);
+      tma_load_3d(sQ, &tmQ, &bars->q_full, h * 64, qt * 128, b);
+      int st = 0; uint32_t ph = 0;
       for (int j = 0; j < n_kv; ++j) {
-        const int ks = j & 1;
-        const uint32_t kph = (j >> 1) & 1;
-        mbar_wait(&k_empty[ks], kph ^ 1);
-        mbar_expect_tx(&k_full[ks], AT_K_BYTES);
-        tma_load_3d(sK + ks * AT_K_BYTES, &tmQK, &k_full[ks], D + h * 64, j * 128, b);
-        mbar_wait(v_empty, (j & 1) ^ 1);
-        mbar_expect_tx(v_full, AT_V_BYTES);
-        tma_load_2d(sV, &tmVT, v_full, j * 128, bh * 64);
-        tma_load_2d(sV + AT_V_BYTES / 2, &tmVT, v_full, j * 128 + 64, bh * 64);
+        mbar_wait(&bars->k_empty[st], ph ^ 1);
+        mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
+        tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, j * AT_KV, b);
+        mbar_wait(&bars->v_empty[st], ph ^ 1);
+        mbar_expect_tx(&bars->v_full[st], AT_V_BYTES);
+        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * 64);
+        if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64);         // both MMAs are M128 N64
       const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
-      const uint64_t dP = make_smem_desc_sw128(smem_u32(sP));
-      const uint64_t dV = make_smem_desc_sw128(smem_u32(sV));
-      mbar_wait(q_full, 0);
-      // S(0) = Q K(0)^T
-      mbar_wait(&k_full[0], 0);
+      mbar_wait(&bars->q_full, 0);
+      // S(0)
+      mbar_wait(&bars->k_full[0], 0);
       tc_fence_after();
       {
         const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, dQ + 2 * k, dK + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[0]);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
+        umma_commit(&bars->s_full[0]);
+        umma_commit(&bars->k_empty[0]);
       }
+      int st = 0; uint32_t ph = 0;                                 // stage / phase of tile j
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait_spin(p_full, j & 1);                            // softmax(j) has consumed S(j) and written P(j)
-        tc_fence_after();
-        if (j + 1 < n_kv) {                                       // S(j+1) first: the next softmax starts while PV(j) runs
-          const int ks = (j + 1) & 1;
-          mbar_wait(&k_full[ks], ((j + 1) >> 1) & 1);
+        if (j + 1 < n_kv) {
+          // S(j+1) into the other S buffer: it held S(j-1), whose softmax finished before p_full(j-1), which this
+          // thread has already waited for (iteration j-1)
+          int st1 = st + 1; uint32_t ph1 = ph;
+          if (st1 == AT_NSTAGE) { st1 = 0; ph1 ^= 1; }
+          mbar_wait(&bars->k_full[st1], ph1);
           tc_fence_after();
-          const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + ks * AT_K_BYTES));
+          const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + st1 * AT_K_BYTES));
+          const uint32_t tS = tmem_base + ((j + 1) & 1) * 64;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, dQ + 2 * k, dK + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-          umma_commit(&k_empty[ks]);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
+          umma_commit(&bars->s_full[(j + 1) & 1]);
+          umma_commit(&bars->k_empty[st1]);
         }
-        mbar_wait(v_full, j & 1);
+        mbar_wait_spin(&bars->p_full[j & 1], (j >> 1) & 1);       // P(j) written, S(j) consumed
+        mbar_wait(&bars->v_full[st], ph);
         tc_fence_after();
+        const uint64_t dP = make_smem_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES));
+        const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int kb = k >> 2, kk = k & 3;
-          umma_bf16_ss(tmem_O, dP + kb * (16384 >> 4) + 2 * kk, dV + kb * (8192 >> 4) + 2 * kk, idesc_o, (j | k) != 0);
-        }
-        umma_commit(v_empty);
-        umma_commit(pv_done);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc, (j | k) != 0);
+        umma_commit(&bars->v_empty[st]);
+        umma_commit(&bars->pv_done[j & 1]);
+        if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -208,22 +216,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8) and row sum
-    uint8_t* p_row = sP + r * 128;
+    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8), row sum
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait_spin(s_full, j & 1);
+      mbar_wait_spin(&bars->s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      const int nvalid = T - j * 128;
-      uint64_t* prev_pv = j > 0 ? pv_done : nullptr;
-      const uint32_t prev_par = (j - 1) & 1;
-      if (nvalid >= 128) softmax_tile<false>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, 128, prev_pv, prev_par, m_used, l);
-      else softmax_tile<true>(tmem_S + lane_off, tmem_O + lane_off, p_row, sw, c_log2, nvalid, prev_pv, prev_par, m_used, l);
+      const int nvalid = T - j * AT_KV;
+      const uint32_t tS = tmem_base + lane_off + (j & 1) * 64;
+      uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
+      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, l);
+      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, l);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&bars->p_full[j & 1]);
     }
-    mbar_wait_spin(pv_done, (n_kv - 1) & 1);
+    mbar_wait_spin(&bars->pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const int tq = qt * 128 + r;
     const float inv = 1.0f / l;
@@ -255,6 +262,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
 }
 
+static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                          const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int Tpad,
                            int n_head, cudaStream_t st) {
   static bool attr_set = false;
@@ -263,33 +280,25 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  EncodeTiledFn enc = get_encode_tiled();
-  if (!enc) return cudaErrorInvalidValue;
   const int D = n_head * 64;
-  CUtensorMap tmQK, tmVT;
+  if (Tpad % AT_KV || Tpad < ((T + AT_KV - 1) / AT_KV) * AT_KV) return cudaErrorInvalidValue;
+  CUtensorMap tmQ, tmK, tmVT;
   {
     cuuint64_t dims[3] = {(cuuint64_t)2 * D, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)2 * D * 2, (cuuint64_t)T * 2 * D * 2};
-    cuuint32_t box[3] = {64, 128, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(qk), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
+    cuuint32_t boxq[3] = {64, 128, 1}, boxk[3] = {64, AT_KV, 1};
+    if (!make_map_bf16(&tmQ, qk, 3, dims, strides, boxq)) return cudaErrorInvalidValue;
+    if (!make_map_bf16(&tmK, qk, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Tpad, (cuuint64_t)B * n_head * 64};
     cuuint64_t strides[1] = {(cuuint64_t)Tpad * 2};
-    cuuint32_t box[2] = {64, 64};
-    cuuint32_t estr[2] = {1, 1};
-    if (enc(&tmVT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(vt), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
+    cuuint32_t box[2] = {AT_KV, 64};
+    if (!make_map_bf16(&tmVT, vt, 2, dims, strides, box)) return cudaErrorInvalidValue;
   }
   const int q_tiles = (T + 127) / 128;
   const float c_log2 = 0.125f * 1.4426950408889634f;
-  attn_tc_kernel<<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQK, tmVT, out, T, D, n_head, q_tiles, c_log2);
+  attn_tc_kernel<<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2);
   return cudaGetLastError();
 }
 

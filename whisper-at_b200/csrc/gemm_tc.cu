@@ -45,8 +45,9 @@ struct GemmTcDev {
 // bias / activation / residual / layout for 32 consecutive columns [n0, n0+32) of output row `row`
 // `stage` (optional, warp-private 32 x 36 floats): fp32 outputs are transposed through it so that global accesses are
 // 128-byte coalesced (8 lanes x 16 B per row) instead of one 16 B access per row.
+// `bias_chunk`: the 32 bias values of this chunk (global, or the per-tile copy the warp prefetched into smem).
 __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok,
-                                                  float* stage = nullptr, int lane = 0) {
+                                                  const float* bias_chunk, float* stage = nullptr, int lane = 0) {
   if (n0 >= g.N) return;
   if (stage != nullptr && (g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32)) {
     float v[32];
@@ -55,13 +56,16 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     if (g.bias) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_chunk + i);
         v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
       }
     }
     if (g.act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+      for (int i = 0; i < 32; i += 2) {
+        const float2 y = gelu_erf_fast2(make_float2(v[i], v[i + 1]));
+        v[i] = y.x; v[i + 1] = y.y;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -100,13 +104,16 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   if (g.bias) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_chunk + i);
       v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
     }
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+    for (int i = 0; i < 32; i += 2) {
+        const float2 y = gelu_erf_fast2(make_float2(v[i], v[i + 1]));
+        v[i] = y.x; v[i + 1] = y.y;
+      }
   }
   if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
@@ -238,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(t_row + c0, r);
         tc_wait_ld();
         if (c0 + 32 == (chalf + 1) * (BN / 2)) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); }
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok);
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? g.bias + n_blk * BN + c0 : nullptr);
       }
     }
   }
@@ -257,7 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // stage-free / accumulator-ready arrivals to both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes.
 constexpr int TC2_STAGES = 5;
 constexpr int TC2_STAGE_BYTES = 2 * TC_A_BYTES;                  // A 128x64 + W-half 128x64
-constexpr int TC2_EPI_STAGE_BYTES = 8 * 32 * 36 * 4;           // 8 epilogue warps x (32 x 36) floats
+constexpr int TC2_EPI_WARP_FLOATS = 32 * 36 + 128;              // per epilogue warp: transpose tile + its 128 bias values
+constexpr int TC2_EPI_STAGE_BYTES = 8 * TC2_EPI_WARP_FLOATS * 4;
 constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + TC2_EPI_STAGE_BYTES;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
@@ -353,6 +361,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      // this warp's 128 bias values -> smem while the MMAs of the tile are still running
+      float* my_stage = epi_stage + (warp - 2) * TC2_EPI_WARP_FLOATS;
+      float* bias_s = my_stage + 32 * 36;
+      if (g.bias) {
+        const int nb = n_blk * BN + chalf * (BN / 2) + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
+        *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+      }
+      __syncwarp();
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
@@ -370,7 +388,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
         }
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, epi_stage + (warp - 2) * (32 * 36), lane);
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * (BN / 2)) : nullptr, my_stage, lane);
       }
     }
   }

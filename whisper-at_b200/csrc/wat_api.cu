@@ -36,15 +36,18 @@ int fail(int code, const char* fmt, ...) {
 // a kernel launch through one of the launchers: counted, error-checked, optionally bracketed by CUDA events
 #define KL(h, expr)                                                                                   \
   do {                                                                                                \
-    const int pi__ = (h)->profiling ? prof_begin((h), #expr) : -1;                                    \
+    const int pi__ = (h)->profiling ? prof_begin((h), #expr) : ((h)->prof_override = -1);                                    \
     cudaError_t e__ = (expr);                                                                         \
     (h)->launches++;                                                                                  \
     if (pi__ >= 0) prof_end((h), pi__);                                                               \
     if (e__ != cudaSuccess) return fail(WAT_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-enum ProfClass { PC_MEL = 0, PC_LAYOUT, PC_GEMM, PC_ATTN, PC_LN, PC_POOL, PC_HEAD_ATTN, PC_MEAN, PC_COUNT };
-const char* const kProfNames[PC_COUNT] = {"mel", "layout", "gemm", "attention", "layernorm", "pool", "head_attention", "mean"};
+enum ProfClass { PC_MEL = 0, PC_LAYOUT, PC_GEMM, PC_ATTN, PC_LN, PC_POOL, PC_HEAD_ATTN, PC_MEAN,
+                 PC_GEMM_QKV, PC_GEMM_OUT, PC_GEMM_FC1, PC_GEMM_FC2, PC_COUNT };
+// "gemm" = conv stem, head and classifier GEMMs; the four encoder-block GEMMs have their own classes
+const char* const kProfNames[PC_COUNT] = {"mel", "layout", "gemm", "attention", "layernorm", "pool", "head_attention", "mean",
+                                          "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2"};
 
 struct ProfRec { int cls; cudaEvent_t a, b; };
 
@@ -98,6 +101,7 @@ struct wat_handle {
   cudaStream_t cur_stream = nullptr;
   std::vector<ProfRec> prof;
   size_t prof_used = 0;
+  int prof_override = -1;                            // class of the next launch (encoder GEMM kinds)
 };
 
 namespace {
@@ -121,7 +125,8 @@ int prof_begin(wat_handle* h, const char* what) {
     h->prof.push_back(r);
   }
   const int i = (int)h->prof_used++;
-  h->prof[i].cls = prof_class(what);
+  h->prof[i].cls = h->prof_override >= 0 ? h->prof_override : prof_class(what);
+  h->prof_override = -1;
   cudaEventRecord(h->prof[i].a, h->cur_stream);
   return i;
 }
@@ -324,6 +329,7 @@ int run_block(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool e
   const int D = w.D, rows = n_seq * T;
   int rc;
   KL(h, launch_layernorm(x, w.ln1_g, w.ln1_b, rows, D, h->xn.p, h->bf16, st));
+  if (encoder) h->prof_override = PC_GEMM_QKV;
   if (h->bf16 && encoder) {
     GemmTc g;
     memset(&g, 0, sizeof(g));
@@ -342,9 +348,12 @@ int run_block(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool e
       KL(h, launch_attn_small(h->qkv.p, h->bf16, h->att.p, h->bf16, n_seq, T, w.H, D / w.H, st));
     }
   }
+  if (encoder) h->prof_override = PC_GEMM_OUT;
   if ((rc = gemm(h, h->att.p, D, w.wo, w.wo_h, w.bo, x, D, x, D, 0, rows, D, D, 0, true, st))) return rc;
   KL(h, launch_layernorm(x, w.ln2_g, w.ln2_b, rows, D, h->xn.p, h->bf16, st));
+  if (encoder) h->prof_override = PC_GEMM_FC1;
   if ((rc = gemm(h, h->xn.p, D, w.w1, w.w1_h, w.b1, h->hbuf.p, 4 * D, nullptr, 0, 0, rows, 4 * D, D, 1, false, st))) return rc;
+  if (encoder) h->prof_override = PC_GEMM_FC2;
   if ((rc = gemm(h, h->hbuf.p, 4 * D, w.w2, w.w2_h, w.b2, x, D, x, D, 0, rows, D, 4 * D, 0, true, st))) return rc;
   return 0;
 }
