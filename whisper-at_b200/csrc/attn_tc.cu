@@ -10,7 +10,9 @@
 //                              waits for P(j); then O += P(j) V(j) (M128 N64 K64) with P(j) read from smem
 //   warps 2..5  softmax      : thread = query row = TMEM lane.  One tcgen05.ld of the 64 scores (kept in registers),
 //                              row max, P = 2^(S*c - m) with one ex2.approx per element, bf16 P into one of two
-//                              128B-swizzled smem tiles, lazy rescale of O in TMEM, final O / l -> bf16
+//                              128B-swizzled smem tiles, lazy rescale of O in TMEM, final O / l -> bf16.
+// The softmax is instruction-issue bound (not MUFU bound), so the row sum l is NOT accumulated by the threads: V^T
+// carries a row of ones and the PV MMA (N = 80) produces l as column 64 of O; scale/subtract uses packed FFMA2.
 // K tail: 1500 = 23*64 + 28; TMA zero-fills rows >= T and those keys are excluded in the last tile only.
 #include "common.cuh"
 #include "kernels.h"
@@ -22,10 +24,10 @@ constexpr int AT_KV = 64;                     // keys per step
 constexpr int AT_NSTAGE = 3;                  // K / V^T pipeline stages
 constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
-constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
+constexpr int AT_V_BYTES = VT_ROWS * AT_KV * 2;  // 10 KB per stage: 64 V^T rows + the ones row (+ zero rows up to 80)
 constexpr int AT_P_BYTES = 128 * AT_KV * 2;   // 16 KB per buffer, 2 buffers
 constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 2 * AT_P_BYTES + 1024 + 256;
-constexpr int AT_TMEM_COLS = 256;             // S0: [0,64)  S1: [64,128)  O: [128,192)
+constexpr int AT_TMEM_COLS = 256;             // S0: [0,64)  S1: [64,128)  O: [128,208): 64 outputs, column 64 = row sum l
 
 struct AttnBars {
   uint64_t q_full;
@@ -42,7 +44,7 @@ struct AttnBars {
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
-                                             int j, AttnBars* bars, float& m_used, float& l) {
+                                             int j, AttnBars* bars, float& m_used) {
   uint32_t a[32], b[32];
   tmem_ld32(tS, a);
   tmem_ld32(tS + 32, b);
@@ -62,56 +64,48 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
-    l *= alpha;
     m_used = m_new;
     if (j > 0) {                                                  // O holds PV(0..j-1): wait for PV(j-1), then rescale
       mbar_wait_spin(&bars->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
+      uint32_t o0[32], o1[32], o2[16];                           // 64 outputs + the row-sum column (+15 zero columns)
       tmem_ld32(tO, o0);
       tmem_ld32(tO + 32, o1);
+      tmem_ld16(tO + 64, o2);
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
         o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
       }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
       tmem_st32(tO, o0);
       tmem_st32(tO + 32, o1);
+      tmem_st16(tO + 64, o2);
       tc_wait_st();
     }
   }
   // The P buffer j&1 was last read by PV(j-2).  No wait is needed: s_full(j), which this thread has observed, was
   // committed by the MMA thread after it issued PV(j-2), and tcgen05.commit tracks every MMA issued before it.
-  const float neg_m = -m_used;
-  // all 64 exponentials first (in place, back-to-back MUFUs), then eight independent partial sums, then pack/store:
-  // keeps the consumer of each MUFU result far behind its issue so the MUFU pipe is never waited on
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float pa = ex2_approx(fmaf(__uint_as_float(a[i]), c_log2, neg_m));
-    float pb = ex2_approx(fmaf(__uint_as_float(b[i]), c_log2, neg_m));
-    if (MASK && i >= nvalid) pa = 0.f;
-    if (MASK && 32 + i >= nvalid) pb = 0.f;
-    a[i] = __float_as_uint(pa);
-    b[i] = __float_as_uint(pb);
-  }
-  float ls[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) ls[e] = 0.f;
+  const float2 c2 = make_float2(c_log2, c_log2), nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
     float p[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 8; e += 2) {
       const int i = g4 * 8 + e;
-      p[e] = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
-      ls[e] += p[e];
+      const float s0 = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
+      const float s1 = __uint_as_float(i < 32 ? a[(i + 1) & 31] : b[(i + 1) & 31]);
+      const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);  // one FFMA2 for two elements
+      p[e] = ex2_approx(x.x);
+      p[e + 1] = ex2_approx(x.y);
+      if (MASK && i >= nvalid) p[e] = 0.f;
+      if (MASK && i + 1 >= nvalid) p[e + 1] = 0.f;
     }
     *reinterpret_cast<uint4*>(p_row + ((g4 ^ sw) << 4)) =
         make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
   }
-  const float lsum = ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
-  l += lsum;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -163,14 +157,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, j * AT_KV, b);
         mbar_wait(&bars->v_empty[st], ph ^ 1);
         mbar_expect_tx(&bars->v_full[st], AT_V_BYTES);
-        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * 64);
+        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * VT_ROWS);
         if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64);         // both MMAs are M128 N64
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64);         // S = Q K^T: M128 N64
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, VT_ROWS);  // O (+ row sum) = P [V | 1]: M128 N80
       const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
       mbar_wait(&bars->q_full, 0);
       // S(0)
@@ -205,7 +200,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t dP = make_smem_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES));
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc, (j | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc_pv, (j | k) != 0);
         umma_commit(&bars->v_empty[st]);
         umma_commit(&bars->pv_done[j & 1]);
         if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
@@ -216,7 +211,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8), row sum
+    float m_used = -INFINITY;                                     // reference max (log2 units, may lag by <= 8)
     const int sw = r & 7;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait_spin(&bars->s_full[j & 1], (j >> 1) & 1);
@@ -224,8 +219,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off + (j & 1) * 64;
       uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
-      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, l);
-      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, l);
+      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used);
+      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars->p_full[j & 1]);
@@ -233,12 +228,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_wait_spin(&bars->pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const int tq = qt * 128 + r;
-    const float inv = 1.0f / l;
     __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;
-    uint32_t v0[32], v1[32];
+    uint32_t v0[32], v1[32], v2[16];
     tmem_ld32(tmem_O + lane_off, v0);
     tmem_ld32(tmem_O + lane_off + 32, v1);
+    tmem_ld16(tmem_O + lane_off + 64, v2);
     tc_wait_ld();
+    const float inv = 1.0f / __uint_as_float(v2[0]);             // column 64 of O: sum_j P_ij (the ones row of V^T)
     if (tq < T) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8)
@@ -260,6 +256,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
+}
+
+__global__ void vt_init_kernel(__nv_bfloat16* vt, int T, int Tpad) {
+  __nv_bfloat16* row = vt + ((long long)blockIdx.x * VT_ROWS + 64) * Tpad;          // the ones row of this (clip, head)
+  for (int t = threadIdx.x; t < Tpad; t += blockDim.x) row[t] = __float2bfloat16_rn(t < T ? 1.0f : 0.0f);
+}
+
+cudaError_t launch_vt_init(__nv_bfloat16* vt, int BH, int T, int Tpad, cudaStream_t st) {
+  vt_init_kernel<<<BH, 256, 0, st>>>(vt, T, Tpad);
+  return cudaGetLastError();
 }
 
 static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
@@ -291,9 +297,9 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
     if (!make_map_bf16(&tmK, qk, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Tpad, (cuuint64_t)B * n_head * 64};
+    cuuint64_t dims[2] = {(cuuint64_t)Tpad, (cuuint64_t)B * n_head * VT_ROWS};
     cuuint64_t strides[1] = {(cuuint64_t)Tpad * 2};
-    cuuint32_t box[2] = {AT_KV, 64};
+    cuuint32_t box[2] = {AT_KV, VT_ROWS};
     if (!make_map_bf16(&tmVT, vt, 2, dims, strides, box)) return cudaErrorInvalidValue;
   }
   const int q_tiles = (T + 127) / 128;

@@ -126,7 +126,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   } else if (g.epi == TC_EPI_QKV) {
     const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
     const int h = vc >> 6, e0 = vc & 63;
-    __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * 64 + e0) * g.seq_Tpad + vtok;
+    __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * VT_ROWS + e0) * g.seq_Tpad + vtok;
 #pragma unroll
     for (int i = 0; i < 32; ++i) vp[(long long)i * g.seq_Tpad] = __float2bfloat16_rn(v[i]);
   } else {

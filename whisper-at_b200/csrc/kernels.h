@@ -88,7 +88,11 @@ struct GemmTc {
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------- attn_tc.cu
-// qk: [B*T, 2D] bf16 (q | k), vt: [B, H, 64, Tpad] bf16, out: [B*T, D] bf16
+// V^T buffer: [B, H, VT_ROWS, Tpad] bf16: rows 0..63 = V transposed (written by the QKV epilogue), row 64 = 1 for
+// keys < T (the PV MMA then also produces the softmax row sum), rows 65..79 and keys >= T = 0.
+constexpr int VT_ROWS = 80;
+cudaError_t launch_vt_init(__nv_bfloat16* vt, int BH, int T, int Tpad, cudaStream_t st);
+// qk: [B*T, 2D] bf16 (q | k), vt as above, out: [B*T, D] bf16
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
                            int Tpad, int n_head, cudaStream_t st);
 

@@ -291,7 +291,14 @@ int ensure_ws(wat_handle* h, int B) {
   if ((rc = grow(h, h->qkv, es * rows_cap * 3 * d))) return rc;
   if ((rc = grow(h, h->att, es * rows_cap * d))) return rc;
   if ((rc = grow(h, h->hbuf, es * rows_cap * 4 * d))) return rc;
-  if (h->bf16 && (rc = grow(h, h->vt, (size_t)2 * Bc * h->H * 64 * 1536, true))) return rc;
+  if (h->bf16) {
+    const size_t before = h->vt.bytes;
+    if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;
+    if (h->vt.bytes != before) {
+      KL(h, launch_vt_init((__nv_bfloat16*)h->vt.p, Bc * h->H, 1500, 1536, 0));
+      CU(cudaDeviceSynchronize());                                // one-off: later work may run on any stream
+    }
+  }
   if ((rc = grow(h, h->logspec, sizeof(float) * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
   if ((rc = grow(h, h->clipmax, sizeof(float) * Bc))) return rc;
   if ((rc = grow(h, h->nvalid, sizeof(int) * Bc))) return rc;
@@ -758,9 +765,10 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
   CU(cudaMalloc(&xh, 2 * rows * D));
   CU(cudaMalloc(&wh, 2 * (size_t)3 * D * D));
   CU(cudaMalloc(&qk, 2 * rows * 2 * D));
-  CU(cudaMalloc(&vt, 2 * (size_t)B * D * Tpad));
+  CU(cudaMalloc(&vt, 2 * (size_t)B * n_head * VT_ROWS * Tpad));
   CU(cudaMalloc(&oh, 2 * rows * D));
-  CU(cudaMemsetAsync(vt, 0, 2 * (size_t)B * D * Tpad, st));
+  CU(cudaMemsetAsync(vt, 0, 2 * (size_t)B * n_head * VT_ROWS * Tpad, st));
+  CU(launch_vt_init(vt, B * n_head, T, Tpad, st));
   CU(launch_f32_to_bf16(x, xh, rows * D, st));
   CU(launch_f32_to_bf16(wqkv, wh, (int64_t)3 * D * D, st));
   GemmTc g;
