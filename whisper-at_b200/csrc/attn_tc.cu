@@ -19,6 +19,9 @@
 
 namespace wat {
 
+// optional per-phase clock trace of one CTA (test hook wat_dbg_attention tc=3): slot = step * 8 + k
+#define AT_TRACE(base, step, k) do { if (tr) tr[(base) + (step) * 8 + (k)] = clock64(); } while (0)
+
 constexpr int AT_THREADS = 192;
 constexpr int AT_KV = 64;                     // keys per step
 constexpr int AT_NSTAGE = 3;                  // K / V^T pipeline stages
@@ -44,11 +47,12 @@ struct AttnBars {
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
-                                             int j, AttnBars* bars, float& m_used) {
+                                             int j, AttnBars* bars, float& m_used, long long* tr) {
   uint32_t a[32], b[32];
   tmem_ld32(tS, a);
   tmem_ld32(tS + 32, b);
   tc_wait_ld();
+  AT_TRACE(0, j, 2);
   // four independent max chains (a single chain of 64 dependent FMNMX costs ~4 cycles each)
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -88,6 +92,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
   }
   // The P buffer j&1 was last read by PV(j-2).  No wait is needed: s_full(j), which this thread has observed, was
   // committed by the MMA thread after it issued PV(j-2), and tcgen05.commit tracks every MMA issued before it.
+  AT_TRACE(0, j, 3);
   const float2 c2 = make_float2(c_log2, c_log2), nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
@@ -111,7 +116,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
-               int q_tiles, float c_log2) {
+               int q_tiles, float c_log2, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -147,46 +152,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp converged (values stay warp-uniform); only the elected lane issues
+    if (elect_one()) {
       mbar_expect_tx(&bars->q_full, AT_Q_BYTES);
       tma_load_3d(sQ, &tmQ, &bars->q_full, h * 64, qt * 128, b);
-      int st = 0; uint32_t ph = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&bars->k_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
-        tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, j * AT_KV, b);
-        mbar_wait(&bars->v_empty[st], ph ^ 1);
-        mbar_expect_tx(&bars->v_full[st], AT_V_BYTES);
-        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * VT_ROWS);
-        if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
-      }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64);         // S = Q K^T: M128 N64
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, VT_ROWS);  // O (+ row sum) = P [V | 1]: M128 N80
-      const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
-      mbar_wait(&bars->q_full, 0);
-      // S(0)
-      mbar_wait(&bars->k_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
-        umma_commit(&bars->s_full[0]);
-        umma_commit(&bars->k_empty[0]);
+    int st = 0; uint32_t ph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&bars->k_empty[st], ph ^ 1);
+      mbar_wait(&bars->v_empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
+        tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, j * AT_KV, b);
+        mbar_expect_tx(&bars->v_full[st], AT_V_BYTES);
+        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * VT_ROWS);
       }
-      int st = 0; uint32_t ph = 0;                                 // stage / phase of tile j
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          // S(j+1) into the other S buffer: it held S(j-1), whose softmax finished before p_full(j-1), which this
-          // thread has already waited for (iteration j-1)
-          int st1 = st + 1; uint32_t ph1 = ph;
-          if (st1 == AT_NSTAGE) { st1 = 0; ph1 ^= 1; }
-          mbar_wait(&bars->k_full[st1], ph1);
-          tc_fence_after();
+      __syncwarp();
+      if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // The whole warp runs the control flow converged and only the elected lane issues tcgen05.mma / commit: issued
+    // from a divergent single-lane region the compiler wraps every MMA in an ELECT/R2UR broadcast loop (~15 extra
+    // instructions each), which made this warp the critical path of the kernel.
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);           // S = Q K^T: M128 N64
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, VT_ROWS);   // O (+ row sum) = P [V | 1]: M128 N80
+    const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
+    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? trace : nullptr;
+    mbar_wait(&bars->q_full, 0);
+    mbar_wait(&bars->k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
+      umma_commit(&bars->s_full[0]);
+      umma_commit(&bars->k_empty[0]);
+    }
+    __syncwarp();
+    int st = 0; uint32_t ph = 0;                                   // stage / phase of tile j
+    for (int j = 0; j < n_kv; ++j) {
+      AT_TRACE(512, j, 0);
+      if (j + 1 < n_kv) {
+        // S(j+1) into the other S buffer: it held S(j-1), whose softmax finished before p_full(j-1), which this
+        // warp has already waited for (iteration j-1)
+        int st1 = st + 1; uint32_t ph1 = ph;
+        if (st1 == AT_NSTAGE) { st1 = 0; ph1 ^= 1; }
+        mbar_wait_spin(&bars->k_full[st1], ph1);
+        tc_fence_after();
+        if (elect_one()) {
           const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + st1 * AT_K_BYTES));
           const uint32_t tS = tmem_base + ((j + 1) & 1) * 64;
 #pragma unroll
@@ -194,36 +208,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&bars->s_full[(j + 1) & 1]);
           umma_commit(&bars->k_empty[st1]);
         }
-        mbar_wait_spin(&bars->p_full[j & 1], (j >> 1) & 1);       // P(j) written, S(j) consumed
-        mbar_wait(&bars->v_full[st], ph);
-        tc_fence_after();
+        __syncwarp();
+      }
+      AT_TRACE(512, j, 1);
+      mbar_wait_spin(&bars->p_full[j & 1], (j >> 1) & 1);         // P(j) written, S(j) consumed
+      AT_TRACE(512, j, 2);
+      mbar_wait_spin(&bars->v_full[st], ph);
+      AT_TRACE(512, j, 3);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t dP = make_smem_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES));
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc_pv, (j | k) != 0);
         umma_commit(&bars->v_empty[st]);
         umma_commit(&bars->pv_done[j & 1]);
-        if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
       }
+      __syncwarp();
+      AT_TRACE(512, j, 4);
+      if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY;                                     // reference max (log2 units, may lag by <= 8)
     const int sw = r & 7;
+    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 64) ? trace : nullptr;
     for (int j = 0; j < n_kv; ++j) {
+      AT_TRACE(0, j, 0);
       mbar_wait_spin(&bars->s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off + (j & 1) * 64;
       uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
-      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used);
-      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used);
+      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, tr);
+      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, tr);
+      AT_TRACE(0, j, 5);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars->p_full[j & 1]);
+      AT_TRACE(0, j, 6);
     }
     mbar_wait_spin(&bars->pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
@@ -279,7 +305,7 @@ static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuin
 }
 
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int Tpad,
-                           int n_head, cudaStream_t st) {
+                           int n_head, cudaStream_t st, long long* trace) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
@@ -304,7 +330,7 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   }
   const int q_tiles = (T + 127) / 128;
   const float c_log2 = 0.125f * 1.4426950408889634f;
-  attn_tc_kernel<<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2);
+  attn_tc_kernel<<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, trace);
   return cudaGetLastError();
 }
 

@@ -180,37 +180,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run converged (all 32 lanes follow the control flow) and only the elected lane issues:
+  // inside a divergent single-lane region the compiler wraps every TMA / tcgen05.mma in an ELECT + R2UR.BROADCAST loop.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait_spin(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(sa);
           const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES);
@@ -218,12 +220,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);   // +32 B per K=16 step
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
         }
-        umma_commit(&tmem_full[as]);
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
     const int chalf = (warp - 2) >> 2;                          // which half of the tile's columns
@@ -307,27 +309,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
-        const int row0 = m_pair * 2 * TC_BM + (int)rank * TC_BM;
-        const int col0 = n_blk * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
+      const int row0 = m_pair * 2 * TC_BM + (int)rank * TC_BM;
+      const int col0 = n_blk * BN + (int)rank * (BN / 2);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE_BYTES);
           const uint32_t bar_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_pair(sa, &tmA, bar_leader, kb * TC_BK, row0);
           tma_load_2d_pair(sb, &tmB, bar_leader, kb * TC_BK, col0);
-          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {                                              // warp-uniform: the leader CTA issues every MMA
       constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -338,21 +340,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_spin(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC2_STAGE_BYTES);
-          const uint64_t a_desc = make_smem_desc_sw128(sa);
-          const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * TC2_STAGE_BYTES);
+            const uint64_t a_desc = make_smem_desc_sw128(sa);
+            const uint64_t b_desc = make_smem_desc_sw128(sa + TC_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_pair(&empty_bar[stage], 3);
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[as], 3);
+          }
+          __syncwarp();
           if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[as], 3);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;

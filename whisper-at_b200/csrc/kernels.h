@@ -94,7 +94,7 @@ constexpr int VT_ROWS = 80;
 cudaError_t launch_vt_init(__nv_bfloat16* vt, int BH, int T, int Tpad, cudaStream_t st);
 // qk: [B*T, 2D] bf16 (q | k), vt as above, out: [B*T, D] bf16
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
-                           int Tpad, int n_head, cudaStream_t st);
+                           int Tpad, int n_head, cudaStream_t st, long long* trace = nullptr);
 
 // driver entry point for cuTensorMapEncodeTiled, resolved once through the runtime
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

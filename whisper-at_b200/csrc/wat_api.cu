@@ -776,7 +776,24 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
   g.A = xh; g.lda = D; g.W = wh; g.bias = bqkv; g.C = qk; g.ldc = 2 * D; g.M = (int)rows; g.N = 3 * D; g.K = D;
   g.epi = TC_EPI_QKV; g.vt = vt; g.seq_T = T; g.seq_Tpad = Tpad; g.n_head = n_head;
   cudaError_t e = launch_gemm_tc(g, sms, st);
-  if (e == cudaSuccess) e = launch_attn_tc(qk, vt, oh, B, T, Tpad, n_head, st);
+  long long* trace = nullptr;
+  if (tc == 3) { CU(cudaMalloc(&trace, 8192)); CU(cudaMemsetAsync(trace, 0, 8192, st)); }
+  if (e == cudaSuccess) e = launch_attn_tc(qk, vt, oh, B, T, Tpad, n_head, st, trace);
+  if (trace) {                                                    // per-phase clock trace of one CTA -> stderr
+    long long ht[1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(ht, trace, 8192, cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    const long long t0 = ht[0];
+    fprintf(stderr, "softmax warp (cycles since start): step | wait_s0 s_ready ld_done max_done . exp_done arrived\n");
+    for (int j = 0; j < (T + 63) / 64; ++j) {
+      fprintf(stderr, "sm %2d |", j);
+      for (int k = 0; k < 7; ++k) fprintf(stderr, " %7lld", ht[j * 8 + k] ? ht[j * 8 + k] - t0 : -1);
+      fprintf(stderr, "   || mma: iter_start qk_issued p_seen v_seen pv_issued |");
+      for (int k = 0; k < 5; ++k) fprintf(stderr, " %7lld", ht[512 + j * 8 + k] ? ht[512 + j * 8 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   cudaError_t e2 = cudaStreamSynchronize(st);
   if (e == cudaSuccess && e2 == cudaSuccess) {
     // bf16 -> fp32 through a tiny identity: reuse the LN-free path by a cast kernel on the host side
