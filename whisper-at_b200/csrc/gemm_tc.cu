@@ -40,6 +40,7 @@ struct GemmTcDev {
   const float* R; long long ldr; int r_mod;
   int M, N, K, act, epi;
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
+  long long* trace;        // optional clock trace of cluster 0 (test hook)
 };
 
 // bias / activation / residual / layout for 32 consecutive columns [n0, n0+32) of output row `row`
@@ -47,7 +48,7 @@ struct GemmTcDev {
 // 128-byte coalesced (8 lanes x 16 B per row) instead of one 16 B access per row.
 // `bias_chunk`: the 32 bias values of this chunk (global, or the per-tile copy the warp prefetched into smem).
 __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok,
-                                                  const float* bias_chunk, float* stage = nullptr, int lane = 0) {
+                                                  const float* bias_chunk, float* stage = nullptr, int lane = 0, long long* tr2 = nullptr) {
   if (n0 >= g.N) return;
   if (stage != nullptr && (g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32)) {
     float v[32];
@@ -60,13 +61,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
         v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
       }
     }
+    if (tr2) tr2[0] = clock64();
     if (g.act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 y = gelu_erf_fast2(make_float2(v[i], v[i + 1]));
-        v[i] = y.x; v[i + 1] = y.y;
-      }
+      for (int i = 0; i < 32; i += 8) gelu_erf_fast8(v + i);
     }
+    if (tr2) tr2[1] = clock64();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     __syncwarp();
@@ -94,6 +94,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
       if (g.epi == TC_EPI_F32_RES) { t.x += res[it].x; t.y += res[it].y; t.z += res[it].z; t.w += res[it].w; }
       if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t;
     }
+    if (tr2) tr2[2] = clock64();
     __syncwarp();
     return;
   }
@@ -110,10 +111,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        const float2 y = gelu_erf_fast2(make_float2(v[i], v[i + 1]));
-        v[i] = y.x; v[i + 1] = y.y;
-      }
+    for (int i = 0; i < 32; i += 8) gelu_erf_fast8(v + i);
   }
   if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
@@ -339,7 +337,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        // Two pipeline stages per iteration: a barrier check costs ~100-170 cycles even when the phase is already
+        // complete, comparable to the 512 tensor cycles of one k-block, so the two try_waits are issued back to back
+        // (their latencies overlap) and 8 MMAs + 2 commits follow in one burst.
+        int kb = 0;
+        for (; kb + 1 < k_blocks; kb += 2) {
+          int stage1 = stage + 1; uint32_t phase1 = phase;
+          if (stage1 == TC2_STAGES) { stage1 = 0; phase1 ^= 1; }
+          const bool ok0 = mbar_try_wait_nohint(&full_bar[stage], phase);
+          const bool ok1 = mbar_try_wait_nohint(&full_bar[stage1], phase1);
+          if (!ok0) mbar_wait_spin(&full_bar[stage], phase);
+          if (!ok1) mbar_wait_spin(&full_bar[stage1], phase1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa0 = smem_u32(smem + stage * TC2_STAGE_BYTES);
+            const uint32_t sa1 = smem_u32(smem + stage1 * TC2_STAGE_BYTES);
+            const uint64_t a0 = make_smem_desc_sw128(sa0), b0 = make_smem_desc_sw128(sa0 + TC_A_BYTES);
+            const uint64_t a1 = make_smem_desc_sw128(sa1), b1 = make_smem_desc_sw128(sa1 + TC_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_ss_pair(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage], 3);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_bf16_ss_pair(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc, 1);
+            umma_commit_pair(&empty_bar[stage1], 3);
+            if (kb + 2 == k_blocks) umma_commit_pair(&tmem_full[as], 3);
+          }
+          __syncwarp();
+          stage = stage1; phase = phase1;
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (kb < k_blocks) {                                      // odd tail
           mbar_wait_spin(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -350,7 +377,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int k = 0; k < TC_BK / 16; ++k)
               umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
             umma_commit_pair(&empty_bar[stage], 3);
-            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[as], 3);
+            umma_commit_pair(&tmem_full[as], 3);
           }
           __syncwarp();
           if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
@@ -374,9 +401,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
       }
+      // residual epilogues are bound by the latency of the residual read (one exposed HBM round trip per chunk):
+      // pull the NEXT tile's residual block of this warp (32 rows x 128 fp32 columns) into L2 now
+      if (g.epi == TC_EPI_F32_RES && g.r_mod == 0) {
+        const int ntile = tile + n_clusters;
+        if (ntile < total_tiles) {
+          const int nn = ntile % n_tiles, nm = ntile / n_tiles;
+          const int prow0 = nm * 2 * TC_BM + (int)rank * TC_BM + q * 32;
+          const int pcol = nn * BN + chalf * (BN / 2) + (lane & 3) * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int prow = prow0 + i * 8 + (lane >> 2);
+            if (prow < g.M && pcol < g.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(g.R + (long long)prow * g.ldr + pcol));
+          }
+        }
+      }
       __syncwarp();
+      long long* tr = (g.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 24) ? g.trace + it * 8 : nullptr;
+      if (tr) tr[0] = clock64();
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (tr) tr[1] = clock64();
       const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -392,7 +438,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
         }
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * (BN / 2)) : nullptr, my_stage, lane);
+        long long* tr2 = (tr && c0 == chalf * (BN / 2) + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
+        if (tr2) tr2[3] = clock64();
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * (BN / 2)) : nullptr, my_stage, lane, tr2);
+        if (tr) tr[2 + (c0 - chalf * (BN / 2)) / 32] = clock64();
       }
     }
   }
@@ -444,6 +493,7 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
   d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  d.trace = nullptr;
   const int m_tiles = (g.M + TC_BM - 1) / TC_BM, n_tiles = (g.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;
@@ -466,6 +516,7 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
   d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  d.trace = g.trace;
   const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   int clusters = num_sms / 2;
   if (clusters > total) clusters = total;

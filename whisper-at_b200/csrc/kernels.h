@@ -84,6 +84,7 @@ struct GemmTc {
   // TC_EPI_QKV only:
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head;  // flat row r -> (b = r / seq_T, t = r % seq_T)
   int force_pair;         // 0: default kernel choice, 1: CTA-pair kernel, -1: single-CTA kernel (tests)
+  long long* trace;       // optional device buffer for a clock trace (tests)
 };
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st);
 

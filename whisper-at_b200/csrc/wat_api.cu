@@ -729,9 +729,27 @@ int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float*
   memset(&g, 0, sizeof(g));
   g.A = Ah; g.lda = K; g.W = Wh; g.bias = bias; g.C = C; g.ldc = N; g.R = R; g.ldr = N; g.r_mod = 0;
   g.M = M; g.N = N; g.K = K; g.act = act; g.epi = R ? TC_EPI_F32_RES : TC_EPI_F32;
-  g.force_pair = tc == 2 ? 1 : -1;                               // tc: 1 = single-CTA kernel, 2 = CTA-pair kernel
+  g.force_pair = tc >= 2 ? 1 : -1;                               // tc: 1 = single-CTA kernel, 2 = CTA-pair kernel, 3 = pair + trace
+  long long* trace = nullptr;
+  if (tc == 3) { CU(cudaMalloc(&trace, 32 * 8 * 8)); CU(cudaMemsetAsync(trace, 0, 32 * 8 * 8, st)); g.trace = trace; }
   cudaError_t e = launch_gemm_tc(g, sms, st);
   cudaError_t e2 = cudaStreamSynchronize(st);
+  if (trace) {
+    long long ht[32 * 8];
+    cudaMemcpy(ht, trace, sizeof(ht), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    fprintf(stderr, "epilogue warp of cluster 0 (cycles): tile | wait_start acc_ready chunk0 chunk1 chunk2 chunk3\n");
+    for (int t = 0; t < 24 && ht[t * 8]; ++t) {
+      fprintf(stderr, "tile %2d |", t);
+      for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", ht[t * 8 + k] ? ht[t * 8 + k] - ht[0] : -1);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "chunk 1 of tiles 8..15: [tmem ld + wait done -> ] bias_done gelu_done stored  (cycles since chunk start)\n");
+    for (int t = 0; t < 8; ++t) {
+      const long long* c = ht + 24 * 8 + t * 4;
+      if (c[3]) fprintf(stderr, "  bias %6lld  gelu %6lld  store %6lld\n", c[0] - c[3], c[1] - c[3], c[2] - c[3]);
+    }
+  }
   cudaFree(Ah); cudaFree(Wh);
   if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "launch_gemm_tc: %s", cudaGetErrorString(e));
   if (e2 != cudaSuccess) return fail(WAT_ERR_CUDA, "gemm_tc execution: %s", cudaGetErrorString(e2));
