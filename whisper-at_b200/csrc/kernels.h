@@ -41,6 +41,10 @@ cudaError_t launch_gemm_f32(const GemmF32& g, cudaStream_t st);
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int D, void* out,
                              bool out_bf16, cudaStream_t st);
 
+// LN of x [B*T, D] fused with the encoder's 20x average pool of the same rows into pooled[b, layer, :, :]
+cudaError_t launch_layernorm_pool20(const float* x, const float* gamma, const float* beta, int B, int T, int D, void* out,
+                                    bool out_bf16, float* pooled, int layer, int L, cudaStream_t st);
+
 // encoder self-attention, fp32, head_dim 64: q/k/v rows at stride ld (same row indexing), n_seq sequences of T
 cudaError_t launch_attn_f32_hd64(const float* q, const float* k, const float* v, long long ld, float* out,
                                  long long ldo, int n_seq, int T, int n_head, cudaStream_t st);

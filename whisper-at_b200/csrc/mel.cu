@@ -4,9 +4,12 @@
 //            -> |X|^2 -> sparse slaney mel projection -> log10(max(.,1e-10)), plus the per-clip maximum.
 //   phase 2  mel_norm_kernel  : max(x, clipmax - 8), (x + 4) / 4, written in the layout the consumer wants.
 //
-// The DFT is evaluated directly (no FFT) with fp64 accumulation over the even/odd-folded frame:
-//   Re X[k] = x[0] + (-1)^k x[200] + sum_{n=1..199} (x[n] + x[400-n]) cos(2 pi n k / 400)
-//   Im X[k] =                      - sum_{n=1..199} (x[n] - x[400-n]) sin(2 pi n k / 400)
+// The DFT is evaluated directly (no FFT) with fp64 accumulation over the twice-folded frame.  First fold (real input):
+//   Re X[k] = x[0] + (-1)^k x[200] + sum_{n=1..199} E[n] cos(2 pi n k / 400),   E[n] = x[n] + x[400-n]
+//   Im X[k] =                      - sum_{n=1..199} O[n] sin(2 pi n k / 400),   O[n] = x[n] - x[400-n]
+// second fold (n <-> 200-n, cos/sin pick up (-1)^k): for n = 1..99 only
+//   sum E cos = E[100] cos(pi k/2) + sum_n (E[n] + (-1)^k E[200-n]) cos(.),  sum O sin = O[100] sin(pi k/2) + sum_n (O[n] - (-1)^k O[200-n]) sin(.)
+// so every bin needs 2 x 99 DFMA instead of 2 x 199; even and odd bins read their own folded sequences.
 // so the result is the exact transform of the fp32 windowed frame (the reference's own fp32 FFT is
 // ~1e-5 away from it in log-mel units; SURVEY.md §7 "mel tolerance is tight").  Only bins 1..199 are
 // evaluated: columns 0 and 200 of the slaney filterbank are zero.
@@ -39,8 +42,8 @@ mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int
                  const float* __restrict__ fb_w,           // packed non-zero weights
                  float* __restrict__ logspec, float* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  EO* eo = reinterpret_cast<EO*>(smem_raw);                               // [MEL_F][201]
-  double2* tw = reinterpret_cast<double2*>(eo + MEL_F * 201);             // [400]
+  EO* eo = reinterpret_cast<EO*>(smem_raw);                               // [2 parities][MEL_F][100]
+  double2* tw = reinterpret_cast<double2*>(eo + 2 * MEL_F * 100);         // [400]
   float* xs = reinterpret_cast<float*>(tw + 400);                         // [MEL_SPAN]
   float* pw = xs + MEL_SPAN;                                              // [MEL_F][MEL_BINS]
   __shared__ float s_max[MEL_THREADS / 32];
@@ -61,44 +64,51 @@ mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int
     xs[i] = (s >= 0 && s < n_valid) ? __ldg(x + s) : 0.f;                 // appended `padding` samples are zero
   }
   __syncthreads();
-  // fold: E[n] = xw[n] + xw[400-n], O[n] = xw[n] - xw[400-n]  (xw = fp32 product, as torch.stft forms it)
-  for (int i = tid; i < MEL_F * 201; i += MEL_THREADS) {
-    int f = i / 201, n = i - f * 201;
+  // fold twice.  eo[(par * MEL_F + f) * 100 + n], n = 1..99: (E[n] +/- E[200-n], O[n] -/+ O[200-n]) for bins of parity par;
+  // slot n = 0 keeps the per-frame specials: par 0 -> (x[0] + x[200], E[100]);  par 1 -> (x[0] - x[200], O[100])
+  for (int i = tid; i < MEL_F * 100; i += MEL_THREADS) {
+    const int f = i / 100, n = i - f * 100;
     const float* fr = xs + f * 160;
-    EO v;
-    if (n == 0) { v.e = (double)__fmul_rn(fr[0], window[0]); v.o = 0.0; }
-    else if (n == 200) { v.e = (double)__fmul_rn(fr[200], window[200]); v.o = 0.0; }
-    else {
-      double a = (double)__fmul_rn(fr[n], window[n]);
-      double b = (double)__fmul_rn(fr[400 - n], window[400 - n]);
-      v.e = a + b; v.o = a - b;
+    auto xw = [&](int j) { return (double)__fmul_rn(fr[j], window[j]); };
+    EO ev, od;
+    if (n == 0) {
+      const double x0 = xw(0), x200 = xw(200), a = xw(100), b = xw(300);
+      ev.e = x0 + x200; ev.o = a + b;                               // E[100]
+      od.e = x0 - x200; od.o = a - b;                               // O[100]
+    } else {
+      const double a = xw(n), b = xw(400 - n), c = xw(200 - n), d = xw(200 + n);
+      const double En = a + b, On = a - b, Em = c + d, Om = c - d;  // m = 200 - n
+      ev.e = En + Em; ev.o = On - Om;
+      od.e = En - Em; od.o = On + Om;
     }
-    eo[i] = v;
+    eo[(0 * MEL_F + f) * 100 + n] = ev;
+    eo[(1 * MEL_F + f) * 100 + n] = od;
   }
   __syncthreads();
 
-  // DFT: thread = 4 bins x 4 frames.  50 bin groups x 5 frame groups = 250 threads.
+  // DFT: thread = 4 bins of one parity x 4 frames.  (25 even + 25 odd bin groups) x 5 frame groups = 250 threads.
   if (tid < 250) {
     const int bg = tid % 50, fg = tid / 50;
-    const int k0 = bg * 4;
+    const int par = bg >= 25;
+    const int kbase = 8 * (bg - 25 * par) + par;                   // bins kbase, kbase+2, kbase+4, kbase+6
     double re[4][4], im[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) { re[a][b] = 0.0; im[a][b] = 0.0; }
     int idx[4] = {0, 0, 0, 0};
-    const EO* base = eo + (fg * 4) * 201;
-    for (int n = 1; n < 200; ++n) {
+    const EO* base = eo + (par * MEL_F + fg * 4) * 100;
+    for (int n = 1; n < 100; ++n) {
       double2 w[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        idx[a] += k0 + a;
+        idx[a] += kbase + 2 * a;
         if (idx[a] >= 400) idx[a] -= 400;
         w[a] = tw[idx[a]];
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        EO v = base[b * 201 + n];
+        const EO v = base[b * 100 + n];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           re[a][b] = fma(v.e, w[a].x, re[a][b]);
@@ -108,13 +118,20 @@ mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int
     }
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const double x0 = base[b * 201 + 0].e, x200 = base[b * 201 + 200].e;
+      const EO sp = base[b * 100];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int k = k0 + a;
-        double r = re[a][b] + x0 + ((k & 1) ? -x200 : x200);
-        double p = r * r + im[a][b] * im[a][b];
-        pw[(fg * 4 + b) * MEL_BINS + k] = (float)p;
+        const int k = kbase + 2 * a;
+        double r, i2;
+        if (!par) {                                                 // even k = 2m: cos(pi k/2) = (-1)^m, sin = 0
+          r = re[a][b] + sp.e + (((k >> 1) & 1) ? -sp.o : sp.o);
+          i2 = im[a][b];
+        } else {                                                    // odd k: cos = 0, sin(pi k/2) = (-1)^((k-1)/2)
+          r = re[a][b] + sp.e;
+          i2 = im[a][b] + ((((k - 1) >> 1) & 1) ? -sp.o : sp.o);
+        }
+        const double p = r * r + i2 * i2;
+        if (k < MEL_BINS) pw[(fg * 4 + b) * MEL_BINS + k] = (float)p;
       }
     }
   }
@@ -239,7 +256,7 @@ __global__ void mel_to_timemajor_kernel(const float* __restrict__ mel, int T, in
 
 // ------------------------------------------------------------------------------------------ host launchers
 size_t mel_power_smem_bytes() {
-  return sizeof(EO) * MEL_F * 201 + sizeof(double2) * 400 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
+  return sizeof(EO) * 2 * MEL_F * 100 + sizeof(double2) * 400 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
 }
 
 cudaError_t launch_mel_power(const MelTables& tb, const float* pcm, long long clip_stride, const int* n_valid_arr,

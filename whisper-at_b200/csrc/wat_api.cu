@@ -110,7 +110,7 @@ int prof_class(const char* s) {
   if (strstr(s, "gemm")) return PC_GEMM;
   if (strstr(s, "attn_small")) return PC_HEAD_ATTN;
   if (strstr(s, "attn")) return PC_ATTN;
-  if (strstr(s, "layernorm")) return PC_LN;
+  if (strstr(s, "layernorm")) return PC_LN;       // includes the fused LN + pool of layers 0..L-2
   if (strstr(s, "pool20")) return PC_POOL;
   if (strstr(s, "group_mean")) return PC_MEAN;
   if (strstr(s, "mel_power") || strstr(s, "mel_norm") || strstr(s, "share_max")) return PC_MEL;
@@ -332,10 +332,13 @@ int gemm(wat_handle* h, const void* A, int64_t lda, const float* Wf, const __nv_
 }
 
 // ResidualAttentionBlock.forward (model.py:128-139) on the fp32 residual stream x [n_seq*T, D]
-int run_block(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st) {
+int run_block(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st,
+              float* pooled = nullptr, int pool_layer = -1) {
   const int D = w.D, rows = n_seq * T;
   int rc;
-  KL(h, launch_layernorm(x, w.ln1_g, w.ln1_b, rows, D, h->xn.p, h->bf16, st));
+  // the first LayerNorm also emits the 20x pooled state of the PREVIOUS layer's output (= this block's input)
+  if (pooled && pool_layer >= 0) KL(h, launch_layernorm_pool20(x, w.ln1_g, w.ln1_b, n_seq, T, D, h->xn.p, h->bf16, pooled, pool_layer, h->L, st));
+  else KL(h, launch_layernorm(x, w.ln1_g, w.ln1_b, rows, D, h->xn.p, h->bf16, st));
   if (encoder) h->prof_override = PC_GEMM_QKV;
   if (h->bf16 && encoder) {
     GemmTc g;
@@ -378,10 +381,9 @@ int run_encoder(wat_handle* h, int B, float* pooled, float* x_out, cudaStream_t 
   KL(h, launch_im2col_k3(h->qkv.p, h->bf16, B, 3000, d, 2, 1500, h->hbuf.p, st));
   if ((rc = gemm(h, h->hbuf.p, 3 * d, h->conv2_w, h->conv2_w_h, h->conv2_b, x, d, h->pos, d, 1500, B * 1500, d, 3 * d, 1, true, st)))
     return rc;
-  for (int l = 0; l < h->L; ++l) {
-    if ((rc = run_block(h, h->enc[l], x, B, 1500, true, st))) return rc;
-    KL(h, launch_pool20(x, B, 1500, d, l, h->L, pooled, st));
-  }
+  for (int l = 0; l < h->L; ++l)
+    if ((rc = run_block(h, h->enc[l], x, B, 1500, true, st, pooled, l - 1))) return rc;
+  KL(h, launch_pool20(x, B, 1500, d, h->L - 1, h->L, pooled, st));   // last layer: nothing downstream reads x again
   if (x_out) KL(h, launch_layernorm(x, h->lnp_g, h->lnp_b, B * 1500, d, x_out, false, st));
   return 0;
 }
