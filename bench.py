@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--res", type=float, default=10)
     ap.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=0, help="clips per internal chunk of the library (0 = the whole per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only: do not force W >= 3")
     args = ap.parse_args()
@@ -131,7 +132,7 @@ def main():
     d, h, L = synth.MODEL_SHAPES[args.model]
     fl = flops_per_clip(d, L, n_mels, args.low, args.res)
     workload = f"whisper-at {args.model} {'TL-TR-512' if args.low else 'TL-TR'} n_mels={n_mels} at_time_res={args.res:g}, 30 s synthetic clips"
-    config = dict(workload=workload, clips_per_gpu=args.batch, global_batch=args.batch * world, at_time_res=args.res,
+    config = dict(workload=workload, clips_per_gpu=args.batch, clips_per_internal_chunk=(args.chunk or args.batch), global_batch=args.batch * world, at_time_res=args.res,
                   parallelism=f"dp{world} (clips sharded, no data-path collective; NCCL all_gather of logits)",
                   l2="inputs+activations per step >> 126 MB L2 (no flush needed)", flops_per_clip=fl["total"])
 
@@ -164,7 +165,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = whisper_at.ModelDimensions(n_mels, 1500, d, h, L, 51865, 448, d, h, L)
-    model = whisper_at.Whisper(dims, at_low_compute=args.low, precision=args.precision, max_batch=args.batch)
+    model = whisper_at.Whisper(dims, at_low_compute=args.low, precision=args.precision, max_batch=(args.chunk or args.batch))
     model.load_state_dict(synth.synth_state_dict(n_mels, d, L, args.low, seed=1, init="lively"), strict=False)
     model = model.to(f"cuda:{local}")
     B = args.batch
