@@ -147,3 +147,51 @@ def test_synth_is_deterministic():
     s2 = synth.synth_state_dict(80, 384, 4, False, seed=1, init="lively")
     assert all(torch.equal(s1[k], s2[k]) for k in s1)
     assert not torch.equal(s1["encoder.conv1.weight"], synth.synth_state_dict(80, 384, 4, False, seed=2, init="lively")["encoder.conv1.weight"])
+
+
+def _fake_checkpoints(tmp_path, low):
+    """An OpenAI-format checkpoint {"dims", "model_state_dict"} (with decoder.* tensors, as the real files have) and the
+    flat AT .pth whose keys already start with at_model. (__init__.py:172-191)."""
+    dims = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=384, n_audio_head=6, n_audio_layer=4, n_vocab=51865,
+                n_text_ctx=448, n_text_state=384, n_text_head=6, n_text_layer=4)
+    sd = synth.synth_state_dict(80, 384, 4, low, seed=3, init="lively")
+    enc = {k: v for k, v in sd.items() if k.startswith("encoder.")}
+    enc["encoder.positional_embedding"] = synth.sinusoid_table(1500, 384)
+    enc["decoder.token_embedding.weight"] = torch.zeros(8, 384)
+    enc["decoder.positional_embedding"] = torch.zeros(448, 384)
+    at = {k: v for k, v in sd.items() if k.startswith("at_model.")}
+    return dims, sd, enc, at
+
+
+@pytest.mark.parametrize("low", [False, True])
+def test_load_model_from_checkpoint_paths(tmp_path, low):
+    dims, sd, enc, at = _fake_checkpoints(tmp_path, low)
+    ck, atp = tmp_path / "enc.pt", tmp_path / "at.pth"
+    torch.save({"dims": dims, "model_state_dict": enc}, ck)
+    torch.save(at, atp)
+    m = whisper_at.load_model(str(ck), device="cpu", at_low_compute=low, at_checkpoint=str(atp))
+    assert isinstance(m, whisper_at.Whisper) and m.at_low_compute == low
+    assert m.at_model.mode == ("tl_down_tr_512_1_8" if low else "tl_tr_1_8")
+    got = m.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+    m2 = whisper_at.load_model(str(ck), device="cpu", at_low_compute=low, at_checkpoint=str(atp), in_memory=True)
+    assert all(torch.equal(m2.state_dict()[k], v) for k, v in sd.items())
+    with pytest.raises(RuntimeError, match="at_checkpoint"):
+        whisper_at.load_model(str(ck), device="cpu")
+    # a head that does not match at_low_compute is rejected by the strict load, as in the reference
+    with pytest.raises(RuntimeError):
+        whisper_at.load_model(str(ck), device="cpu", at_low_compute=not low, at_checkpoint=str(atp))
+
+
+def test_load_model_by_name_uses_the_reference_cache_layout(tmp_path):
+    """Official names resolve to <download_root>/<basename(url)> exactly as the reference's _download caches them
+    (__init__.py:68-81), so a cache populated by the reference is picked up without network access."""
+    dims, sd, enc, at = _fake_checkpoints(tmp_path, False)
+    torch.save({"dims": dims, "model_state_dict": enc}, tmp_path / "tiny.pt")
+    torch.save(at, tmp_path / "tiny_ori.pth?dl=1")
+    m = whisper_at.load_model("tiny", device="cpu", download_root=str(tmp_path))
+    assert all(torch.equal(m.state_dict()[k], v) for k, v in sd.items())
+    assert m.dims.n_audio_layer == 4 and m.precision == "bf16"
+    with pytest.raises(RuntimeError, match="could not download"):
+        whisper_at.load_model("base", device="cpu", download_root=str(tmp_path / "empty"))

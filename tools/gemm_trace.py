@@ -13,3 +13,5 @@ M = 1500 * 64
 for name, N, K, act, res in (("fc1-like (gelu, f32 out)", 5120, 1280, 1, False), ("out-proj (f32 residual)", 1280, 1280, 0, True), ("fc2 (f32 residual)", 1280, 5120, 0, True)):
     print("=====", name, file=sys.stderr); sys.stderr.flush()
     run(M, N, K, act, res, 2); run(M, N, K, act, res, 3)
+print("===== fc1 bf16+gelu (16 epilogue warps)", file=sys.stderr); sys.stderr.flush()
+run(M, 5120, 1280, 1, False, 4)

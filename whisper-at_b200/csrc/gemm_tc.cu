@@ -99,6 +99,27 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     return;
   }
   if (!row_ok) return;
+  if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
+    // 8 columns at a time: bias, GELU, pack, one 16-byte store (keeps the live set small: this path also runs in the
+    // 16-epilogue-warp kernel, which has ~96 registers per thread)
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
+      if (g.bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_chunk + i);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_chunk + i + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (g.act == 1) gelu_erf_fast8(v);
+      *reinterpret_cast<uint4*>(cp + i) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    return;
+  }
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -113,14 +134,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
 #pragma unroll
     for (int i = 0; i < 32; i += 8) gelu_erf_fast8(v + i);
   }
-  if (g.epi == TC_EPI_BF16 || (g.epi == TC_EPI_QKV && n0 < 2 * g.D)) {
-    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      uint4 u = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
-                           pack_bf16(v[i + 6], v[i + 7]));
-      *reinterpret_cast<uint4*>(cp + i) = u;
-    }
+  if (false) {
   } else if (g.epi == TC_EPI_QKV) {
     const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
     const int h = vc >> 6, e0 = vc & 63;
@@ -264,13 +278,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // stage-free / accumulator-ready arrivals to both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes.
 constexpr int TC2_STAGES = 5;
 constexpr int TC2_STAGE_BYTES = 2 * TC_A_BYTES;                  // A 128x64 + W-half 128x64
-constexpr int TC2_EPI_WARP_FLOATS = 32 * 36 + 128;              // per epilogue warp: transpose tile + its 128 bias values
-constexpr int TC2_EPI_STAGE_BYTES = 8 * TC2_EPI_WARP_FLOATS * 4;
-constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + TC2_EPI_STAGE_BYTES;
+// EW = epilogue warps: 8 (two per TMEM lane quadrant, 128 columns each; fp32 outputs use a per-warp transpose tile) or
+// 16 (four per quadrant, 64 columns each) for the bf16 + GELU epilogue, whose per-tile latency with 8 warps (~13k
+// cycles) exceeds the tile's 10k MMA cycles at K = 1280.
+template <int EW> struct Tc2Cfg {
+  static constexpr int THREADS = 64 + 32 * EW;
+  static constexpr int COLS = 256 / (EW / 4);                    // columns per epilogue warp
+  static constexpr int WARP_FLOATS = (EW == 8 ? 32 * 36 : 0) + COLS;   // transpose tile (8-warp kernel only) + bias slice
+  static constexpr int SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + EW * WARP_FLOATS * 4;
+};
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<EW>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
   constexpr int BN = 256;
+  using Cfg2 = Tc2Cfg<EW>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -297,7 +319,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }   // 8 warps x 2 CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EW); }   // EW warps x 2 CTAs
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
@@ -386,29 +408,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    const int chalf = (warp - 2) >> 2;                             // which column slice of the tile (COLS wide)
+    constexpr int COLS = Cfg2::COLS;
     int it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
       const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       // this warp's 128 bias values -> smem while the MMAs of the tile are still running
-      float* my_stage = epi_stage + (warp - 2) * TC2_EPI_WARP_FLOATS;
-      float* bias_s = my_stage + 32 * 36;
-      if (g.bias) {
-        const int nb = n_blk * BN + chalf * (BN / 2) + lane * 4;
+      float* my_stage = epi_stage + (warp - 2) * Cfg2::WARP_FLOATS;
+      float* bias_s = my_stage + (EW == 8 ? 32 * 36 : 0);
+      if (g.bias && lane * 4 < COLS) {
+        const int nb = n_blk * BN + chalf * COLS + lane * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
       }
       // residual epilogues are bound by the latency of the residual read (one exposed HBM round trip per chunk):
       // pull the NEXT tile's residual block of this warp (32 rows x 128 fp32 columns) into L2 now
-      if (g.epi == TC_EPI_F32_RES && g.r_mod == 0) {
+      if (EW == 8 && g.epi == TC_EPI_F32_RES && g.r_mod == 0) {
         const int ntile = tile + n_clusters;
         if (ntile < total_tiles) {
           const int nn = ntile % n_tiles, nm = ntile / n_tiles;
           const int prow0 = nm * 2 * TC_BM + (int)rank * TC_BM + q * 32;
-          const int pcol = nn * BN + chalf * (BN / 2) + (lane & 3) * 32;
+          const int pcol = nn * BN + chalf * COLS + (lane & 3) * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int prow = prow0 + i * 8 + (lane >> 2);
@@ -429,19 +452,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int vb = 0, vtok = 0;
       if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
 #pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+      for (int c0 = chalf * COLS; c0 < (chalf + 1) * COLS; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
         tc_wait_ld();
-        if (c0 + 32 == (chalf + 1) * (BN / 2)) {
+        if (c0 + 32 == (chalf + 1) * COLS) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
         }
-        long long* tr2 = (tr && c0 == chalf * (BN / 2) + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
+        long long* tr2 = (tr && c0 == chalf * COLS + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
         if (tr2) tr2[3] = clock64();
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * (BN / 2)) : nullptr, my_stage, lane, tr2);
-        if (tr) tr[2 + (c0 - chalf * (BN / 2)) / 32] = clock64();
+        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, EW == 8 ? my_stage : nullptr, lane, tr2);
+        if (tr) tr[2 + (c0 - chalf * COLS) / 32] = clock64();
       }
     }
   }
@@ -502,10 +525,12 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
 }
 
 
+template <int EW>
 static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
+  using Cfg2 = Tc2Cfg<EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -520,7 +545,7 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   int clusters = num_sms / 2;
   if (clusters > total) clusters = total;
-  gemm_tc2_kernel<<<2 * clusters, TC_THREADS, TC2_SMEM_BYTES, st>>>(tmA, tmB, d);
+  gemm_tc2_kernel<EW><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, d);
   return cudaGetLastError();
 }
 
@@ -539,7 +564,11 @@ cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   if ((g.K & 7) || (g.lda & 7) || (g.N & 31) || (g.ldc & 7)) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
   if (g.epi == TC_EPI_QKV && ((g.N % 3) || ((g.N / 3) & 63) || g.seq_T <= 0)) return cudaErrorInvalidValue;
-  if (g.N % 256 == 0 && (g.force_pair > 0 || (g.force_pair == 0 && pair_mode() && g.M >= 256))) return launch_tc2(g, num_sms, st);
+  if (g.N % 256 == 0 && (g.force_pair > 0 || (g.force_pair == 0 && pair_mode() && g.M >= 256))) {
+    static const int wide = getenv("WAT_GEMM_EW16") ? atoi(getenv("WAT_GEMM_EW16")) : 1;
+    if (wide && g.epi == TC_EPI_BF16 && g.act == 1) return launch_tc2<16>(g, num_sms, st);     // GELU epilogue
+    return launch_tc2<8>(g, num_sms, st);
+  }
   if (g.N % 256 == 0) return launch_tc<256>(g, num_sms, st);
   if (g.N % 128 == 0) return launch_tc<128>(g, num_sms, st);
   return cudaErrorInvalidValue;

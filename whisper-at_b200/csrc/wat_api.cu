@@ -732,8 +732,10 @@ int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float*
   g.A = Ah; g.lda = K; g.W = Wh; g.bias = bias; g.C = C; g.ldc = N; g.R = R; g.ldr = N; g.r_mod = 0;
   g.M = M; g.N = N; g.K = K; g.act = act; g.epi = R ? TC_EPI_F32_RES : TC_EPI_F32;
   g.force_pair = tc >= 2 ? 1 : -1;                               // tc: 1 = single-CTA kernel, 2 = CTA-pair kernel, 3 = pair + trace
+  __nv_bfloat16* Cb = nullptr;                                   // tc 4: trace of the bf16 (+GELU) epilogue kernel; C is not written
+  if (tc == 4) { CU(cudaMalloc(&Cb, sizeof(__nv_bfloat16) * (size_t)M * N)); g.C = Cb; g.epi = TC_EPI_BF16; g.R = nullptr; }
   long long* trace = nullptr;
-  if (tc == 3) { CU(cudaMalloc(&trace, 32 * 8 * 8)); CU(cudaMemsetAsync(trace, 0, 32 * 8 * 8, st)); g.trace = trace; }
+  if (tc >= 3) { CU(cudaMalloc(&trace, 32 * 8 * 8)); CU(cudaMemsetAsync(trace, 0, 32 * 8 * 8, st)); g.trace = trace; }
   cudaError_t e = launch_gemm_tc(g, sms, st);
   cudaError_t e2 = cudaStreamSynchronize(st);
   if (trace) {
@@ -753,6 +755,7 @@ int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float*
     }
   }
   cudaFree(Ah); cudaFree(Wh);
+  if (Cb) cudaFree(Cb);
   if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "launch_gemm_tc: %s", cudaGetErrorString(e));
   if (e2 != cudaSuccess) return fail(WAT_ERR_CUDA, "gemm_tc execution: %s", cudaGetErrorString(e2));
   return WAT_OK;
