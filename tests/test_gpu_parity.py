@@ -350,3 +350,25 @@ def test_permutation_and_chunking_invariance():
     short = m.tag_batch(a, at_time_res=10, n_valid=nv)
     one = m.tag_batch(a[1:2, :80000].contiguous(), at_time_res=10)
     assert torch.equal(short[1], one[0])
+
+
+def test_pooled_feature_export_vs_oracle(tmp_path):
+    from whisper_at import features
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="fp32")
+    clip = synth.synth_clip(5)[:160000]                           # a 10 s clip
+    feat = features.pooled_features(m, clip, seconds=10.0)
+    assert feat.shape == (4, 25, 384) and feat.dtype == np.float32
+    ref = O.encoder_pooled(O.log_mel_clip(clip)[None], sd, h)[0][:, :25]
+    assert max_abs(feat, ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+    features.save_feature_npz(str(tmp_path / "c.npz"), feat)
+    assert np.array_equal(features.load_feature_npz(str(tmp_path / "c.npz")), feat)
+
+
+def test_int16_pcm_ingest_is_bit_identical():
+    """load_audio yields int16 / 32768 (audio.py:63); feeding the int16 samples directly must give the same logits"""
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="bf16")
+    pcm16 = (synth.synth_batch(3, start=1).clamp(-1, 1) * 32767).round().to(torch.int16)
+    as_float = pcm16.to(torch.float32) / 32768.0
+    ref = m.tag_batch(as_float.cuda(), at_time_res=10)
+    assert torch.equal(m.tag_batch(pcm16.cuda(), at_time_res=10), ref)
+    assert torch.equal(m.tag_batch_host(pcm16, at_time_res=10), ref.cpu())

@@ -195,3 +195,18 @@ def test_load_model_by_name_uses_the_reference_cache_layout(tmp_path):
     assert m.dims.n_audio_layer == 4 and m.precision == "bf16"
     with pytest.raises(RuntimeError, match="could not download"):
         whisper_at.load_model("base", device="cpu", download_root=str(tmp_path / "empty"))
+
+
+def test_feature_file_format_matches_reference_loader(tmp_path):
+    """the npz written for the TL-TR training recipe is what dataloader_feat.py:97-125 reads: key arr_0, [L, T', d],
+    padded / cut to 25 steps by the loader"""
+    from whisper_at import features
+    feat = np.random.default_rng(0).standard_normal((4, 25, 384)).astype(np.float32)
+    path = str(tmp_path / "clip.npz")
+    features.save_feature_npz(path, feat)
+    z = np.load(path)
+    assert z.files == ["arr_0"] and z["arr_0"].dtype == np.float32
+    assert np.array_equal(features.load_feature_npz(path), feat)
+    t = torch.Tensor(z["arr_0"])                                   # the reference loader's next steps
+    t = t[:, :25, :] if t.shape[1] >= 25 else torch.nn.functional.pad(t, (0, 0, 0, 25 - t.shape[1]))
+    assert tuple(t.shape) == (4, 25, 384)

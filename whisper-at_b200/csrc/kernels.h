@@ -17,7 +17,7 @@ struct MelTables {
   int* fb_off = nullptr;        // [n_mels + 1]
   float* fb_w = nullptr;        // [nnz]
 };
-cudaError_t launch_mel_power(const MelTables& tb, const float* pcm, long long clip_stride, const int* n_valid_arr,
+cudaError_t launch_mel_power(const MelTables& tb, const void* pcm, bool pcm_i16, long long clip_stride, const int* n_valid_arr,
                              int n_valid_all, int n_pad, int B, int n_frames, int n_store, int frames_alloc,
                              float* logspec, float* clip_max, cudaStream_t st);
 cudaError_t launch_share_max(float* clip_max, int B, cudaStream_t st);

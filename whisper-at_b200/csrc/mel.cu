@@ -33,7 +33,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 // grid: (ceil(n_frames/MEL_F), B).  logspec: [B, frames_alloc, n_mels] (frames >= n_store only feed the max)
 __global__ void __launch_bounds__(MEL_THREADS)
-mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int* __restrict__ n_valid_arr,
+mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_stride, const int* __restrict__ n_valid_arr,
                  int n_valid_all, int n_pad, int n_frames, int n_store, int frames_alloc, int n_mels,
                  const double2* __restrict__ twiddle,      // [400] (cos, sin)(2 pi j / 400)
                  const float* __restrict__ window,         // [400] periodic hann
@@ -53,7 +53,9 @@ mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int
   const int tid = threadIdx.x;
   const int n_valid = n_valid_arr ? n_valid_arr[clip] : n_valid_all;
   const int n_total = n_valid + n_pad;
-  const float* x = pcm + (long long)clip * clip_stride;
+  // fp32 samples, or int16 PCM scaled by 1/32768 exactly as the reference's load_audio does (audio.py:63)
+  const float* xf = reinterpret_cast<const float*>(pcm) + (long long)clip * clip_stride;
+  const short* xi = reinterpret_cast<const short*>(pcm) + (long long)clip * clip_stride;
 
   for (int i = tid; i < 400; i += MEL_THREADS) tw[i] = twiddle[i];
   const int s0 = t0 * 160 - 200;
@@ -61,7 +63,9 @@ mel_power_kernel(const float* __restrict__ pcm, long long clip_stride, const int
     int s = s0 + i;
     if (s < 0) s = -s;                                                    // reflect about sample 0
     if (s >= n_total) s = 2 * (n_total - 1) - s;                          // reflect about the padded end
-    xs[i] = (s >= 0 && s < n_valid) ? __ldg(x + s) : 0.f;                 // appended `padding` samples are zero
+    float smp = 0.f;                                                      // appended `padding` samples are zero
+    if (s >= 0 && s < n_valid) smp = pcm_i16 ? (float)__ldg(xi + s) * (1.0f / 32768.0f) : __ldg(xf + s);
+    xs[i] = smp;
   }
   __syncthreads();
   // fold twice.  eo[(par * MEL_F + f) * 100 + n], n = 1..99: (E[n] +/- E[200-n], O[n] -/+ O[200-n]) for bins of parity par;
@@ -259,7 +263,7 @@ size_t mel_power_smem_bytes() {
   return sizeof(EO) * 2 * MEL_F * 100 + sizeof(double2) * 400 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
 }
 
-cudaError_t launch_mel_power(const MelTables& tb, const float* pcm, long long clip_stride, const int* n_valid_arr,
+cudaError_t launch_mel_power(const MelTables& tb, const void* pcm, bool pcm_i16, long long clip_stride, const int* n_valid_arr,
                              int n_valid_all, int n_pad, int B, int n_frames, int n_store, int frames_alloc,
                              float* logspec, float* clip_max, cudaStream_t st) {
   static bool attr_set = false;
@@ -271,7 +275,7 @@ cudaError_t launch_mel_power(const MelTables& tb, const float* pcm, long long cl
   }
   fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(clip_max, -INFINITY, B);
   dim3 grid((n_frames + MEL_F - 1) / MEL_F, B);
-  mel_power_kernel<<<grid, MEL_THREADS, smem, st>>>(pcm, clip_stride, n_valid_arr, n_valid_all, n_pad, n_frames, n_store,
+  mel_power_kernel<<<grid, MEL_THREADS, smem, st>>>(pcm, pcm_i16 ? 1 : 0, clip_stride, n_valid_arr, n_valid_all, n_pad, n_frames, n_store,
                                                     frames_alloc, tb.n_mels, tb.twiddle, tb.window, tb.fb_start,
                                                     tb.fb_off, tb.fb_w, logspec, clip_max);
   return cudaGetLastError();

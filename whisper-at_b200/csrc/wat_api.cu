@@ -433,7 +433,7 @@ int check_ready(wat_handle* h) {
   return 0;
 }
 
-int mel_frames(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid_host, int n_samples, int n_pad,
+int mel_frames(wat_handle* h, const void* pcm, bool i16, int64_t clip_stride, const int32_t* n_valid_host, int n_samples, int n_pad,
                int B, int n_frames, cudaStream_t st) {
   // frames that can see signal: t <= (n + 199) / 160 ; they all feed the per-clip max (audio.py:155)
   const int n_total_frames = (n_samples + n_pad) / 160;
@@ -447,7 +447,7 @@ int mel_frames(wat_handle* h, const float* pcm, int64_t clip_stride, const int32
     CU(cudaMemcpyAsync(h->nvalid.p, n_valid_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
     nv_dev = (const int*)h->nvalid.p;
   }
-  KL(h, launch_mel_power(h->mel, pcm, clip_stride, nv_dev, n_samples, n_pad, B, n_scan, n_frames, n_frames,
+  KL(h, launch_mel_power(h->mel, pcm, i16, clip_stride, nv_dev, n_samples, n_pad, B, n_scan, n_frames, n_frames,
                          (float*)h->logspec.p, (float*)h->clipmax.p, st));
   h->launches++;                                                 // the clip_max fill kernel
   return 0;
@@ -604,7 +604,7 @@ int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32
   if ((rc = grow(h, ls, sizeof(float) * (size_t)B * n_frames * h->cfg.n_mels))) return rc;
   if ((rc = grow(h, cm, sizeof(float) * B))) return rc;
   if ((rc = grow(h, nv, sizeof(int) * B))) return rc;
-  if ((rc = mel_frames(h, pcm, clip_stride, n_valid, n_samples, n_pad, B, n_frames, st))) return rc;
+  if ((rc = mel_frames(h, pcm, false, clip_stride, n_valid, n_samples, n_pad, B, n_frames, st))) return rc;
   if (clamp_scope == 1 && B > 1) KL(h, launch_share_max((float*)cm.p, B, st));
   KL(h, launch_mel_norm((const float*)ls.p, (const float*)cm.p, B, n_frames, n_frames, h->cfg.n_mels, 0, mel_out, st));
   return WAT_OK;
@@ -637,21 +637,21 @@ int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int
   return run_head(h, pooled, B, t_total, t_start, t_len, dw, logits_out, (cudaStream_t)stream);
 }
 
-int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples, int32_t B,
-            int32_t dw, float* logits_out, void* stream) {
+static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                    int32_t B, int32_t dw, float* logits_out, cudaStream_t st) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!pcm || !logits_out || B < 1 || n_samples < 1 || n_samples > 480000) return fail(WAT_ERR_INVALID, "bad argument (clips are <= 480000 samples)");
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
-  cudaStream_t st = (cudaStream_t)stream;
   h->cur_stream = st;
   const int cb = h->cfg.max_batch;
   const int S = (75 + dw - 1) / dw;
+  const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
   for (int b0 = 0; b0 < B; b0 += cb) {
     const int nb = std::min(cb, B - b0);
     if ((rc = ensure_ws(h, nb))) return rc;
-    if ((rc = mel_frames(h, pcm + (int64_t)b0 * clip_stride, clip_stride, n_valid ? n_valid + b0 : nullptr, n_samples, 480000, nb,
-                         3000, st))) return rc;
+    const void* p0 = reinterpret_cast<const char*>(pcm) + (size_t)b0 * clip_stride * esz;
+    if ((rc = mel_frames(h, p0, i16, clip_stride, n_valid ? n_valid + b0 : nullptr, n_samples, 480000, nb, 3000, st))) return rc;
     KL(h, launch_mel_norm((const float*)h->logspec.p, (const float*)h->clipmax.p, nb, 3000, 3000, h->cfg.n_mels, h->bf16 ? 2 : 1,
                           h->melT.p, st));
     if ((rc = run_encoder(h, nb, (float*)h->pooled.p, nullptr, st))) return rc;
@@ -660,8 +660,8 @@ int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t*
   return WAT_OK;
 }
 
-int wat_tag_host(wat_handle* h, const float* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
-                 int32_t B, int32_t dw, float* logits_host) {
+static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t clip_stride, const int32_t* n_valid,
+                         int32_t n_samples, int32_t B, int32_t dw, float* logits_host) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!pcm_host || !logits_host || B < 1 || n_samples < 1 || n_samples > 480000 || clip_stride < n_samples)
@@ -669,14 +669,31 @@ int wat_tag_host(wat_handle* h, const float* pcm_host, int64_t clip_stride, cons
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
   const int S = (75 + dw - 1) / dw;
   cudaStream_t st = h->own_stream;
-  const size_t pcm_bytes = sizeof(float) * ((size_t)(B - 1) * clip_stride + n_samples);
+  const size_t pcm_bytes = (i16 ? sizeof(int16_t) : sizeof(float)) * ((size_t)(B - 1) * clip_stride + n_samples);
   if ((rc = grow(h, h->pcm_stage, pcm_bytes))) return rc;
   if ((rc = grow(h, h->logits, sizeof(float) * (size_t)B * S * h->cfg.n_class))) return rc;
   CU(cudaMemcpyAsync(h->pcm_stage.p, pcm_host, pcm_bytes, cudaMemcpyHostToDevice, st));
-  if ((rc = wat_tag(h, (const float*)h->pcm_stage.p, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st))) return rc;
+  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st))) return rc;
   CU(cudaMemcpyAsync(logits_host, h->logits.p, sizeof(float) * (size_t)B * S * h->cfg.n_class, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return WAT_OK;
+}
+
+int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples, int32_t B,
+            int32_t dw, float* logits_out, void* stream) {
+  return tag_impl(h, pcm, false, clip_stride, n_valid, n_samples, B, dw, logits_out, (cudaStream_t)stream);
+}
+int wat_tag_pcm16(wat_handle* h, const int16_t* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples, int32_t B,
+                  int32_t dw, float* logits_out, void* stream) {
+  return tag_impl(h, pcm, true, clip_stride, n_valid, n_samples, B, dw, logits_out, (cudaStream_t)stream);
+}
+int wat_tag_host(wat_handle* h, const float* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                 int32_t B, int32_t dw, float* logits_host) {
+  return tag_host_impl(h, pcm_host, false, clip_stride, n_valid, n_samples, B, dw, logits_host);
+}
+int wat_tag_host_pcm16(wat_handle* h, const int16_t* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                       int32_t B, int32_t dw, float* logits_host) {
+  return tag_host_impl(h, pcm_host, true, clip_stride, n_valid, n_samples, B, dw, logits_host);
 }
 
 int64_t wat_workspace_bytes(const wat_handle* h) { return h ? h->ws_bytes : 0; }

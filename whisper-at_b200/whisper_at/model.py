@@ -247,11 +247,12 @@ class Whisper(nn.Module):
     # ------------------------------------------------------------------ batched tagging (the throughput path)
     def tag_batch(self, audio: Tensor, at_time_res=10, n_valid: Optional[np.ndarray] = None,
                   precision: Optional[str] = None) -> Tensor:
-        """audio [B, n<=480000] fp32 on the model's device -> logits [B, S, 527] on device.
-        One fused libwat call: mel -> encoder -> TL-TR (wat_tag)."""
+        """audio [B, n<=480000] fp32 (or int16 PCM) on the model's device -> logits [B, S, 527] on device.
+        One fused libwat call: mel -> encoder -> TL-TR (wat_tag / wat_tag_pcm16)."""
         eng = self.engine(precision)
         assert audio.ndim == 2 and audio.shape[1] <= 480000
-        a = audio.to(eng.device, torch.float32).contiguous()
+        i16 = audio.dtype == torch.int16
+        a = audio.to(eng.device).contiguous() if i16 else audio.to(eng.device, torch.float32).contiguous()
         B, n = a.shape
         dw = int(at_time_res * 2.5)
         S = math.ceil(75 / dw)
@@ -263,7 +264,8 @@ class Whisper(nn.Module):
         with torch.cuda.device(eng.device):
             out = torch.empty((B, S, 527), dtype=torch.float32, device=eng.device)
             st = torch.cuda.current_stream().cuda_stream
-            _lib.check(eng.L.wat_tag(eng.h, a.data_ptr(), n, nv, n, B, dw, out.data_ptr(), st))
+            fn = eng.L.wat_tag_pcm16 if i16 else eng.L.wat_tag
+            _lib.check(fn(eng.h, a.data_ptr(), n, nv, n, B, dw, out.data_ptr(), st))
         return out
 
     def tag_batch_host(self, audio: Tensor, at_time_res=10, out: Optional[Tensor] = None,
@@ -272,7 +274,8 @@ class Whisper(nn.Module):
         speed); returns CPU logits.  H2D copy, compute and D2H copy all happen inside the call."""
         eng = self.engine(precision)
         assert audio.ndim == 2 and audio.shape[1] <= 480000 and not audio.is_cuda
-        a = audio.to(torch.float32).contiguous()
+        i16 = audio.dtype == torch.int16                           # 16-bit PCM: half the H2D bytes (wat_tag_host_pcm16)
+        a = audio.contiguous() if i16 else audio.to(torch.float32).contiguous()
         B, n = a.shape
         dw = int(at_time_res * 2.5)
         S = math.ceil(75 / dw)
@@ -280,7 +283,8 @@ class Whisper(nn.Module):
             out = torch.empty((B, S, 527), dtype=torch.float32)
         assert out.shape == (B, S, 527) and out.dtype == torch.float32 and out.is_contiguous() and not out.is_cuda
         with torch.cuda.device(eng.device):
-            _lib.check(eng.L.wat_tag_host(eng.h, a.data_ptr(), n, None, n, B, dw, out.data_ptr()))
+            fn = eng.L.wat_tag_host_pcm16 if i16 else eng.L.wat_tag_host
+            _lib.check(fn(eng.h, a.data_ptr(), n, None, n, B, dw, out.data_ptr()))
         return out
 
     def kernel_launches(self) -> int:
