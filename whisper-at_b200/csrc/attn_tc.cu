@@ -22,21 +22,22 @@ namespace wat {
 // optional per-phase clock trace of one CTA (test hook wat_dbg_attention tc=3): slot = step * 8 + k
 #define AT_TRACE(base, step, k) do { if (tr) tr[(base) + (step) * 8 + (k)] = clock64(); } while (0)
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 160;                // 1 control warp (TMA + MMA issue) + 4 softmax warps
 constexpr int AT_KV = 64;                     // keys per step
-constexpr int AT_NSTAGE = 3;                  // K / V^T pipeline stages
+constexpr int AT_NSTAGE = 2;                  // K / V^T pipeline stages
 constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
-constexpr int AT_V_BYTES = VT_ROWS * AT_KV * 2;  // 10 KB per stage: 64 V^T rows + the ones row (+ zero rows up to 80)
-constexpr int AT_P_BYTES = 128 * AT_KV * 2;   // 16 KB per buffer, 2 buffers
-constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 2 * AT_P_BYTES + 1024 + 256;
-constexpr int AT_TMEM_COLS = 256;             // S0: [0,64)  S1: [64,128)  O: [128,208): 64 outputs, column 64 = row sum l
+constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
+constexpr int AT_P_BYTES = 128 * AT_KV * 2;   // 16 KB, single buffer
+constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + AT_P_BYTES + 1024 + 256;
+constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)   (three CTAs per SM share the 512 columns)
 
 struct AttnBars {
   uint64_t q_full;
   uint64_t k_full[AT_NSTAGE], k_empty[AT_NSTAGE];
   uint64_t v_full[AT_NSTAGE], v_empty[AT_NSTAGE];
-  uint64_t s_full[2];       // S buffer written by the MMA
+  uint64_t s_full[2];       // S written by the MMA (only [0] is used)
+  uint64_t s_free;          // the 128 softmax threads hold S(j) in registers: the MMA warp may overwrite S
   uint64_t p_full[2];       // P buffer written by the 128 softmax threads (and S buffer fully read)
   uint64_t pv_done[2];      // PV(j) finished: P buffer j&1 reusable, O stable
   uint32_t tmem_slot;
@@ -47,11 +48,13 @@ struct AttnBars {
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
-                                             int j, AttnBars* bars, float& m_used, long long* tr) {
+                                             int j, AttnBars* bars, float& m_used, float& l, long long* tr) {
   uint32_t a[32], b[32];
   tmem_ld32(tS, a);
   tmem_ld32(tS + 32, b);
   tc_wait_ld();
+  tc_fence_before();
+  mbar_arrive(&bars->s_free);                                     // S is in registers: Q K(j+1)^T may overwrite the buffer
   AT_TRACE(0, j, 2);
   // four independent max chains (a single chain of 64 dependent FMNMX costs ~4 cycles each)
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -64,36 +67,30 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
   }
   float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   mx *= c_log2;
+  // the single P tile is read by PV(j-1) and a rescale touches O: both need PV(j-1) to be finished
+  if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }
   const bool need = mx > m_used + 8.0f;
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
+    l *= alpha;
     m_used = m_new;
-    if (j > 0) {                                                  // O holds PV(0..j-1): wait for PV(j-1), then rescale
-      mbar_wait_spin(&bars->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-      tc_fence_after();
-      uint32_t o0[32], o1[32], o2[16];                           // 64 outputs + the row-sum column (+15 zero columns)
-      tmem_ld32(tO, o0);
-      tmem_ld32(tO + 32, o1);
-      tmem_ld16(tO + 64, o2);
-      tc_wait_ld();
+    if (j > 0) {
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld32(tO + hh * 32, o);
+        tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-        o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + hh * 32, o);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
-      tmem_st32(tO, o0);
-      tmem_st32(tO + 32, o1);
-      tmem_st16(tO + 64, o2);
       tc_wait_st();
     }
   }
-  // The P buffer j&1 was last read by PV(j-2).  No wait is needed: s_full(j), which this thread has observed, was
-  // committed by the MMA thread after it issued PV(j-2), and tcgen05.commit tracks every MMA issued before it.
   AT_TRACE(0, j, 3);
   const float2 c2 = make_float2(c_log2, c_log2), nm2 = make_float2(-m_used, -m_used);
+  float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0, ls2 = ls0, ls3 = ls0;
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
     float p[8];
@@ -108,12 +105,18 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
       if (MASK && i >= nvalid) p[e] = 0.f;
       if (MASK && i + 1 >= nvalid) p[e + 1] = 0.f;
     }
+    ls0 = __fadd2_rn(ls0, make_float2(p[0], p[1]));               // packed row-sum partials
+    ls1 = __fadd2_rn(ls1, make_float2(p[2], p[3]));
+    ls2 = __fadd2_rn(ls2, make_float2(p[4], p[5]));
+    ls3 = __fadd2_rn(ls3, make_float2(p[6], p[7]));
     *reinterpret_cast<uint4*>(p_row + ((g4 ^ sw) << 4)) =
         make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
   }
+  const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
+  l += t.x + t.y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
                int q_tiles, float c_log2, long long* __restrict__ trace) {
@@ -124,7 +127,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sK = sQ + AT_Q_BYTES;
   uint8_t* sV = sK + AT_NSTAGE * AT_K_BYTES;
   uint8_t* sP = sV + AT_NSTAGE * AT_V_BYTES;
-  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 2 * AT_P_BYTES);
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + AT_P_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % q_tiles;
@@ -142,6 +145,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); mbar_init(&bars->pv_done[s], 1); }
+    mbar_init(&bars->s_free, 128);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
@@ -149,36 +153,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 64;
 
   if (warp == 0) {
-    // whole warp converged (values stay warp-uniform); only the elected lane issues
+    // Control warp: TMA producer and MMA issuer in one converged warp (only the elected lane issues).  Five warps per CTA
+    // keep three CTAs on an SM at <= 4 warps per sub-partition, i.e. a 128-register budget for the softmax warps.
+    // Prefetch distances: K two tiles ahead, V^T one tile ahead, so none of the stage-free waits below ever blocks long.
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);           // both MMAs are M128 N64
+    const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
+    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? trace : nullptr;
     if (elect_one()) {
       mbar_expect_tx(&bars->q_full, AT_Q_BYTES);
       tma_load_3d(sQ, &tmQ, &bars->q_full, h * 64, qt * 128, b);
+      mbar_expect_tx(&bars->k_full[0], AT_K_BYTES);
+      tma_load_3d(sK, &tmK, &bars->k_full[0], D + h * 64, 0, b);
+      mbar_expect_tx(&bars->v_full[0], AT_V_BYTES);
+      tma_load_2d(sV, &tmVT, &bars->v_full[0], 0, bh * VT_ROWS);
+      if (n_kv > 1) {
+        mbar_expect_tx(&bars->k_full[1], AT_K_BYTES);
+        tma_load_3d(sK + AT_K_BYTES, &tmK, &bars->k_full[1], D + h * 64, AT_KV, b);
+      }
     }
     __syncwarp();
-    int st = 0; uint32_t ph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&bars->k_empty[st], ph ^ 1);
-      mbar_wait(&bars->v_empty[st], ph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
-        tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, j * AT_KV, b);
-        mbar_expect_tx(&bars->v_full[st], AT_V_BYTES);
-        tma_load_2d(sV + st * AT_V_BYTES, &tmVT, &bars->v_full[st], j * AT_KV, bh * VT_ROWS);
-      }
-      __syncwarp();
-      if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
-    }
-  } else if (warp == 1) {
-    // The whole warp runs the control flow converged and only the elected lane issues tcgen05.mma / commit: issued
-    // from a divergent single-lane region the compiler wraps every MMA in an ELECT/R2UR broadcast loop (~15 extra
-    // instructions each), which made this warp the critical path of the kernel.
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64);           // S = Q K^T: M128 N64
-    constexpr uint32_t idesc_pv = make_idesc_bf16(128, VT_ROWS);   // O (+ row sum) = P [V | 1]: M128 N80
-    const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
-    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? trace : nullptr;
     mbar_wait(&bars->q_full, 0);
     mbar_wait(&bars->k_full[0], 0);
     tc_fence_after();
@@ -190,77 +186,110 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       umma_commit(&bars->k_empty[0]);
     }
     __syncwarp();
-    int st = 0; uint32_t ph = 0;                                   // stage / phase of tile j
+    if (n_kv > 2) {                                                // K(2) into stage 0 as soon as Q K(0)^T has read it
+      mbar_wait_spin(&bars->k_empty[0], 0);
+      if (elect_one()) {
+        mbar_expect_tx(&bars->k_full[0], AT_K_BYTES);
+        tma_load_3d(sK, &tmK, &bars->k_full[0], D + h * 64, 2 * AT_KV, b);
+      }
+      __syncwarp();
+    }
     for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
       AT_TRACE(512, j, 0);
+      // every barrier check costs ~150 cycles even when the phase is complete, so the checks of each group are issued
+      // back to back (latencies overlap): {k_full, s_free} -> QK(j+1);  {p_full, v_full} -> PV(j);  {v_empty, k_empty} -> TMA
       if (j + 1 < n_kv) {
-        // S(j+1) into the other S buffer: it held S(j-1), whose softmax finished before p_full(j-1), which this
-        // warp has already waited for (iteration j-1)
-        int st1 = st + 1; uint32_t ph1 = ph;
-        if (st1 == AT_NSTAGE) { st1 = 0; ph1 ^= 1; }
-        mbar_wait_spin(&bars->k_full[st1], ph1);
+        const bool okk = mbar_try_wait_nohint(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        const bool oks = mbar_try_wait_nohint(&bars->s_free, j & 1);
+        if (!okk) mbar_wait_spin(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        AT_TRACE(512, j, 5);
+        if (!oks) mbar_wait_spin(&bars->s_free, j & 1);           // the softmax threads hold S(j) in registers
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + st1 * AT_K_BYTES));
-          const uint32_t tS = tmem_base + ((j + 1) & 1) * 64;
+          const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + (st ^ 1) * AT_K_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tS, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
-          umma_commit(&bars->s_full[(j + 1) & 1]);
-          umma_commit(&bars->k_empty[st1]);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
+          umma_commit(&bars->s_full[0]);
+          umma_commit(&bars->k_empty[st ^ 1]);
         }
         __syncwarp();
       }
       AT_TRACE(512, j, 1);
-      mbar_wait_spin(&bars->p_full[j & 1], (j >> 1) & 1);         // P(j) written, S(j) consumed
-      AT_TRACE(512, j, 2);
-      mbar_wait_spin(&bars->v_full[st], ph);
+      {
+        const bool okp = mbar_try_wait_nohint(&bars->p_full[0], j & 1);
+        const bool okv = mbar_try_wait_nohint(&bars->v_full[st], ph);
+        if (!okp) mbar_wait_spin(&bars->p_full[0], j & 1);        // P(j) written
+        AT_TRACE(512, j, 2);
+        if (!okv) mbar_wait_spin(&bars->v_full[st], ph);
+      }
       AT_TRACE(512, j, 3);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dP = make_smem_desc_sw128(smem_u32(sP + (j & 1) * AT_P_BYTES));
+        const uint64_t dP = make_smem_desc_sw128(smem_u32(sP));
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc_pv, (j | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc, (j | k) != 0);
         umma_commit(&bars->v_empty[st]);
-        umma_commit(&bars->pv_done[j & 1]);
+        umma_commit(&bars->pv_done[0]);
       }
       __syncwarp();
+      // prefetches, off the softmax's critical path and a full step ahead of their use (a K tile takes > 1000 cycles
+      // to arrive with three CTAs per SM): V^T(j+1) into the stage PV(j-1) released, K(j+3) into Q K(j+1)^T's
+      {
+        const bool need_v = j + 1 < n_kv, need_k = j + 3 < n_kv;
+        const uint32_t ph1 = ((j + 1) >> 1) & 1;
+        const bool okve = (need_v && j >= 1) ? mbar_try_wait_nohint(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1) : true;
+        const bool okke = need_k ? mbar_try_wait_nohint(&bars->k_empty[st ^ 1], ph1) : true;
+        if (!okve) mbar_wait_spin(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1);
+        if (!okke) mbar_wait_spin(&bars->k_empty[st ^ 1], ph1);
+        if (elect_one()) {
+          if (need_v) {
+            mbar_expect_tx(&bars->v_full[st ^ 1], AT_V_BYTES);
+            tma_load_2d(sV + (st ^ 1) * AT_V_BYTES, &tmVT, &bars->v_full[st ^ 1], (j + 1) * AT_KV, bh * VT_ROWS);
+          }
+          if (need_k) {
+            mbar_expect_tx(&bars->k_full[st ^ 1], AT_K_BYTES);
+            tma_load_3d(sK + (st ^ 1) * AT_K_BYTES, &tmK, &bars->k_full[st ^ 1], D + h * 64, (j + 3) * AT_KV, b);
+          }
+        }
+        __syncwarp();
+      }
       AT_TRACE(512, j, 4);
-      if (++st == AT_NSTAGE) { st = 0; ph ^= 1; }
     }
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_used = -INFINITY;                                     // reference max (log2 units, may lag by <= 8)
+    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8), row sum
     const int sw = r & 7;
-    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 64) ? trace : nullptr;
+    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 32) ? trace : nullptr;
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
-      mbar_wait_spin(&bars->s_full[j & 1], (j >> 1) & 1);
+      mbar_wait_spin(&bars->s_full[0], j & 1);
       tc_fence_after();
       AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
-      const uint32_t tS = tmem_base + lane_off + (j & 1) * 64;
-      uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
-      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, tr);
-      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, tr);
+      const uint32_t tS = tmem_base + lane_off;
+      uint8_t* p_row = sP + r * 128;
+      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, l, tr);
+      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, l, tr);
       AT_TRACE(0, j, 5);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[j & 1]);
+      mbar_arrive(&bars->p_full[0]);
       AT_TRACE(0, j, 6);
     }
-    mbar_wait_spin(&bars->pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+    mbar_wait_spin(&bars->pv_done[0], (n_kv - 1) & 1);
     tc_fence_after();
     const int tq = qt * 128 + r;
     __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;
-    uint32_t v0[32], v1[32], v2[16];
+    uint32_t v0[32], v1[32];
     tmem_ld32(tmem_O + lane_off, v0);
     tmem_ld32(tmem_O + lane_off + 32, v1);
-    tmem_ld16(tmem_O + lane_off + 64, v2);
     tc_wait_ld();
-    const float inv = 1.0f / __uint_as_float(v2[0]);             // column 64 of O: sum_j P_ij (the ones row of V^T)
+    const float inv = 1.0f / l;
     if (tq < T) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8)
@@ -325,7 +354,7 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   {
     cuuint64_t dims[2] = {(cuuint64_t)Tpad, (cuuint64_t)B * n_head * VT_ROWS};
     cuuint64_t strides[1] = {(cuuint64_t)Tpad * 2};
-    cuuint32_t box[2] = {AT_KV, VT_ROWS};
+    cuuint32_t box[2] = {AT_KV, 64};
     if (!make_map_bf16(&tmVT, vt, 2, dims, strides, box)) return cudaErrorInvalidValue;
   }
   const int q_tiles = (T + 127) / 128;

@@ -291,30 +291,9 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + er);
 }
 
-// two GELUs at once with packed f32x2 FMA-pipe instructions (sm_100 FFMA2/FMUL2): same A-S 7.1.26 erf, written as
-//   q = 0.5 * poly(t) * 2^(-x^2 / (2 ln 2)) = Phi(-|x|),  gelu(x) = max(x, 0) - |x * q|
-// ~10 issue slots per element instead of ~16
-__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
-  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 d = __ffma2_rn(ax, make_float2(0.23164189f, 0.23164189f), make_float2(1.0f, 1.0f));   // 0.3275911 / sqrt(2)
-  float2 t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
-  float2 p = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
-  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
-  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
-  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
-  p = __fmul2_rn(p, t);
-  float2 a = __fmul2_rn(x, x);
-  a = __fmul2_rn(a, make_float2(-0.72134752044448170f, -0.72134752044448170f));                       // -log2(e) / 2
-  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-  float2 q = __fmul2_rn(p, e);
-  q = __fmul2_rn(q, make_float2(0.5f, 0.5f));
-  const float2 r = __fmul2_rn(x, q);
-  return make_float2(fmaxf(x.x, 0.f) - fabsf(r.x), fmaxf(x.y, 0.f) - fabsf(r.y));
-}
-
-// Eight GELUs written stage by stage over four f32x2 pairs, so that every dependent step (rcp -> 5 x FFMA2 -> ... ) has
+// Eight exact-erf GELUs with packed f32x2 FMA-pipe instructions (sm_100 FFMA2/FMUL2), same A-S 7.1.26 erf written as
+//   q = 0.5 * poly(t) * 2^(-x^2 / (2 ln 2)) = Phi(-|x|),  gelu(x) = max(x, 0) - |x * q|     (~10 issue slots per element)
+// and laid out stage by stage over four f32x2 pairs, so that every dependent step (rcp -> 5 x FFMA2 -> ... ) has
 // four independent instructions next to each other: issued pair after pair the chain latency (~100 cycles) is exposed.
 __device__ __forceinline__ void gelu_erf_fast8(float* v) {
   float2 x[4], t[4], p[4], e[4];
@@ -347,30 +326,6 @@ __device__ __forceinline__ void gelu_erf_fast8(float* v) {
     v[2 * k] = fmaxf(x[k].x, 0.f) - fabsf(r.x);
     v[2 * k + 1] = fmaxf(x[k].y, 0.f) - fabsf(r.y);
   }
-}
-
-// Single-MUFU variant: Phi(-|x|) = h(|x|) * 2^(-x^2 log2(e)/2) with h(u) = erfc(u/sqrt2) e^{u^2/2} / 2 fitted by a degree-10
-// polynomial in t = u/3 - 1 on u in [0, 6] (max |gelu error| 3.6e-6, 100x below bf16 resolution; beyond |x| = 6 the
-// Gaussian factor underflows the result to x or -0 as it should).  One MUFU and no dependent rcp per element.
-__device__ __forceinline__ float2 gelu_erf_poly2(float2 x) {
-  const float2 u = make_float2(fminf(fabsf(x.x), 6.0f), fminf(fabsf(x.y), 6.0f));
-  const float2 t = __ffma2_rn(u, make_float2(1.0f / 3.0f, 1.0f / 3.0f), make_float2(-1.0f, -1.0f));
-  float2 p = __ffma2_rn(t, make_float2(8.348427435e-03f, 8.348427435e-03f), make_float2(-1.375725723e-02f, -1.375725723e-02f));
-  p = __ffma2_rn(p, t, make_float2(1.108191628e-03f, 1.108191628e-03f));
-  p = __ffma2_rn(p, t, make_float2(-3.003236505e-03f, -3.003236505e-03f));
-  p = __ffma2_rn(p, t, make_float2(2.488031246e-02f, 2.488031246e-02f));
-  p = __ffma2_rn(p, t, make_float2(-3.614321952e-02f, -3.614321952e-02f));
-  p = __ffma2_rn(p, t, make_float2(4.404180939e-02f, 4.404180939e-02f));
-  p = __ffma2_rn(p, t, make_float2(-6.145184827e-02f, -6.145184827e-02f));
-  p = __ffma2_rn(p, t, make_float2(8.249675593e-02f, 8.249675593e-02f));
-  p = __ffma2_rn(p, t, make_float2(-1.032495579e-01f, -1.032495579e-01f));
-  p = __ffma2_rn(p, t, make_float2(1.215126673e-01f, 1.215126673e-01f));
-  float2 a = __fmul2_rn(x, x);
-  a = __fmul2_rn(a, make_float2(-0.72134752044448170f, -0.72134752044448170f));                       // -log2(e) / 2
-  const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-  const float2 q = __fmul2_rn(p, e);
-  const float2 r = __fmul2_rn(x, q);
-  return make_float2(fmaxf(x.x, 0.f) - fabsf(r.x), fmaxf(x.y, 0.f) - fabsf(r.y));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
