@@ -28,9 +28,9 @@ constexpr int AT_NSTAGE = 2;                  // K / V^T pipeline stages
 constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
 constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
-constexpr int AT_P_BYTES = 128 * AT_KV * 2;   // 16 KB, single buffer
-constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + AT_P_BYTES + 1024 + 256;
-constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)   (three CTAs per SM share the 512 columns)
+constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 1024 + 256;
+constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)
+constexpr int AT_TMEM_P_COLS = 32;            // P as packed bf16 pairs, a second allocation: 3 x (128 + 32) <= 512 columns per SM
 
 struct AttnBars {
   uint64_t q_full;
@@ -40,14 +40,14 @@ struct AttnBars {
   uint64_t s_free;          // the 128 softmax threads hold S(j) in registers: the MMA warp may overwrite S
   uint64_t p_full[2];       // P buffer written by the 128 softmax threads (and S buffer fully read)
   uint64_t pv_done[2];      // PV(j) finished: P buffer j&1 reusable, O stable
-  uint32_t tmem_slot;
+  uint32_t tmem_slot, tmem_slot_p;
 };
 
 // One KV tile of the online softmax for one query row (thread == TMEM lane).  The reference max m_used is only moved
 // when the true max exceeds it by more than 2^8 (lazy rescale): P stays <= 256, the O accumulator in TMEM is
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
-__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* p_row, int sw, float c_log2, int nvalid,
+__device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t tP, float c_log2, int nvalid,
                                              int j, AttnBars* bars, float& m_used, float& l, long long* tr) {
   uint32_t a[32], b[32];
   tmem_ld32(tS, a);
@@ -109,9 +109,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint8_t* 
     ls1 = __fadd2_rn(ls1, make_float2(p[2], p[3]));
     ls2 = __fadd2_rn(ls2, make_float2(p[4], p[5]));
     ls3 = __fadd2_rn(ls3, make_float2(p[6], p[7]));
-    *reinterpret_cast<uint4*>(p_row + ((g4 ^ sw) << 4)) =
-        make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    tmem_st4(tP + g4 * 4, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
   }
+  tc_wait_st();
   const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
   l += t.x + t.y;
 }
@@ -126,8 +126,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
   uint8_t* sV = sK + AT_NSTAGE * AT_K_BYTES;
-  uint8_t* sP = sV + AT_NSTAGE * AT_V_BYTES;
-  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + AT_P_BYTES);
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sV + AT_NSTAGE * AT_V_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % q_tiles;
@@ -148,12 +147,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(&bars->s_free, 128);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS);
+    tmem_alloc(&bars->tmem_slot_p, AT_TMEM_P_COLS);
+    tmem_relinquish();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tmem_O = tmem_base + 64;
+  const uint32_t tmem_P = bars->tmem_slot_p;
 
   if (warp == 0) {
     // Control warp: TMA producer and MMA issuer in one converged warp (only the elected lane issues).  Five warps per CTA
@@ -227,10 +231,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       AT_TRACE(512, j, 3);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dP = make_smem_desc_sw128(smem_u32(sP));
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_O, dP + 2 * k, dV + 2 * k, idesc, (j | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_O, tmem_P + 8 * k, dV + 2 * k, idesc, (j | k) != 0);
         umma_commit(&bars->v_empty[st]);
         umma_commit(&bars->pv_done[0]);
       }
@@ -263,7 +266,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8), row sum
-    const int sw = r & 7;
     long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 32) ? trace : nullptr;
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
@@ -272,11 +274,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off;
-      uint8_t* p_row = sP + r * 128;
-      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, p_row, sw, c_log2, AT_KV, j, bars, m_used, l, tr);
-      else softmax_tile<true>(tS, tmem_O + lane_off, p_row, sw, c_log2, nvalid, j, bars, m_used, l, tr);
+      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, bars, m_used, l, tr);
+      else softmax_tile<true>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, bars, m_used, l, tr);
       AT_TRACE(0, j, 5);
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars->p_full[0]);
       AT_TRACE(0, j, 6);
@@ -310,7 +310,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_P, AT_TMEM_P_COLS); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
 }
 
 __global__ void vt_init_kernel(__nv_bfloat16* vt, int T, int Tpad) {

@@ -825,7 +825,7 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
     cudaMemcpy(ht, trace, 8192, cudaMemcpyDeviceToHost);
     cudaFree(trace);
     const long long t0 = ht[0];
-    fprintf(stderr, "softmax warp (cycles since start): step | wait_s0 s_ready ld_done max_done . exp_done arrived\n");
+    fprintf(stderr, "softmax warp (cycles since start): step | wait_s0 s_ready ld_done max_done halfA exp_done arrived\n");
     for (int j = 0; j < (T + 63) / 64; ++j) {
       fprintf(stderr, "sm %2d |", j);
       for (int k = 0; k < 7; ++k) fprintf(stderr, " %7lld", ht[j * 8 + k] ? ht[j * 8 + k] - t0 : -1);
