@@ -5,7 +5,8 @@ B, T, H = 8, 1500, 20
 D = 64 * H
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B * T, D, generator=g).cuda()
-w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D) * 2.0).cuda()
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 2.0
+w = (torch.randn(3 * D, D, generator=g) / math.sqrt(D) * scale).cuda()
 b = torch.randn(3 * D, generator=g).cuda()
 out = torch.empty(B * T, D, device="cuda")
 for tc in (1, 3):

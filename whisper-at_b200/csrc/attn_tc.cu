@@ -29,6 +29,7 @@ constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
 constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
 constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 1024 + 256;
+constexpr float AT_LAZY_LOG2 = 24.0f;         // rescale O only when a row max grows by more than 2^24
 constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)
 constexpr int AT_TMEM_P_COLS = 32;            // P as packed bf16 pairs, a second allocation: 3 x (128 + 32) <= 512 columns per SM
 
@@ -44,7 +45,8 @@ struct AttnBars {
 };
 
 // One KV tile of the online softmax for one query row (thread == TMEM lane).  The reference max m_used is only moved
-// when the true max exceeds it by more than 2^8 (lazy rescale): P stays <= 256, the O accumulator in TMEM is
+// when the true max exceeds it by more than 2^24 (lazy rescale; P is bf16 and O / l are fp32, so a P of up to 2^24 loses
+// nothing: every term carries the same 2^-m_used factor and it cancels in O / l): the O accumulator in TMEM is
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t tP, float c_log2, int nvalid,
@@ -67,10 +69,10 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   }
   float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   mx *= c_log2;
-  // the single P tile is read by PV(j-1) and a rescale touches O: both need PV(j-1) to be finished
-  if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }
-  const bool need = mx > m_used + 8.0f;
+  const bool need = mx > m_used + AT_LAZY_LOG2;
   if (__any_sync(0xffffffffu, need)) {
+    if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }   // a rescale touches O: PV(j-1) must be done
+    if (tr) tr[j * 8 + 7] = 1;
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
     l *= alpha;
@@ -91,6 +93,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   AT_TRACE(0, j, 3);
   const float2 c2 = make_float2(c_log2, c_log2), nm2 = make_float2(-m_used, -m_used);
   float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0, ls2 = ls0, ls3 = ls0;
+  uint32_t pk[32];                                                // P(j) as bf16 pairs; takes over the registers S(j) frees
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {
     float p[8];
@@ -109,8 +112,15 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
     ls1 = __fadd2_rn(ls1, make_float2(p[2], p[3]));
     ls2 = __fadd2_rn(ls2, make_float2(p[4], p[5]));
     ls3 = __fadd2_rn(ls3, make_float2(p[6], p[7]));
-    tmem_st4(tP + g4 * 4, pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    pk[g4 * 4 + 0] = pack_bf16(p[0], p[1]);
+    pk[g4 * 4 + 1] = pack_bf16(p[2], p[3]);
+    pk[g4 * 4 + 2] = pack_bf16(p[4], p[5]);
+    pk[g4 * 4 + 3] = pack_bf16(p[6], p[7]);
   }
+  AT_TRACE(0, j, 4);
+  // the single P tile in TMEM is read by PV(j-1): only the store waits for it, the exponentials above overlapped it
+  if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }
+  tmem_st32(tP, pk);
   tc_wait_st();
   const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
   l += t.x + t.y;
@@ -265,7 +275,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q = warp & 3;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 8), row sum
+    float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 24), row sum
     long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 32) ? trace : nullptr;
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
