@@ -20,7 +20,7 @@
 namespace wat {
 
 // optional per-phase clock trace of one CTA (test hook wat_dbg_attention tc=3): slot = step * 8 + k
-#define AT_TRACE(base, step, k) do { if (tr) tr[(base) + (step) * 8 + (k)] = clock64(); } while (0)
+#define AT_TRACE(base, step, k) do { if (TRACE && tr) tr[(base) + (step) * 8 + (k)] = clock64(); } while (0)
 
 constexpr int AT_THREADS = 160;                // 1 control warp (TMA + MMA issue) + 4 softmax warps
 constexpr int AT_KV = 64;                     // keys per step
@@ -48,9 +48,10 @@ struct AttnBars {
 // when the true max exceeds it by more than 2^24 (lazy rescale; P is bf16 and O / l are fp32, so a P of up to 2^24 loses
 // nothing: every term carries the same 2^-m_used factor and it cancels in O / l): the O accumulator in TMEM is
 // rescaled only on those rare steps, and the final O / l is unchanged.  MASK handles the ragged last tile.
-template <bool MASK>
+template <bool MASK, bool TRACE>
 __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t tP, float c_log2, int nvalid,
-                                             int j, AttnBars* bars, float& m_used, float& l, long long* tr) {
+                                             int j, int n_kv, AttnBars* bars, float& m_used, float& l, bool& s_next,
+                                             long long* tr) {
   uint32_t a[32], b[32];
   tmem_ld32(tS, a);
   tmem_ld32(tS + 32, b);
@@ -72,7 +73,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   const bool need = mx > m_used + AT_LAZY_LOG2;
   if (__any_sync(0xffffffffu, need)) {
     if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }   // a rescale touches O: PV(j-1) must be done
-    if (tr) tr[j * 8 + 7] = 1;
+    if (TRACE && tr) tr[j * 8 + 7] = 1;
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
     l *= alpha;
@@ -119,13 +120,20 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   }
   AT_TRACE(0, j, 4);
   // the single P tile in TMEM is read by PV(j-1): only the store waits for it, the exponentials above overlapped it
-  if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }
+  // (the check of S(j+1) is issued with it: an mbarrier check costs ~150 cycles even when the phase is complete)
+  {
+    const bool okp = j > 0 ? mbar_test_wait(&bars->pv_done[0], (j - 1) & 1) : true;
+    s_next = j + 1 < n_kv ? mbar_test_wait(&bars->s_full[0], (j + 1) & 1) : true;
+    if (!okp) mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1);
+    tc_fence_after();
+  }
   tmem_st32(tP, pk);
   tc_wait_st();
   const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
   l += t.x + t.y;
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(AT_THREADS, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
@@ -215,8 +223,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // every barrier check costs ~150 cycles even when the phase is complete, so the checks of each group are issued
       // back to back (latencies overlap): {k_full, s_free} -> QK(j+1);  {p_full, v_full} -> PV(j);  {v_empty, k_empty} -> TMA
       if (j + 1 < n_kv) {
-        const bool okk = mbar_try_wait_nohint(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
-        const bool oks = mbar_try_wait_nohint(&bars->s_free, j & 1);
+        const bool okk = mbar_test_wait(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        const bool oks = mbar_test_wait(&bars->s_free, j & 1);
         if (!okk) mbar_wait_spin(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
         AT_TRACE(512, j, 5);
         if (!oks) mbar_wait_spin(&bars->s_free, j & 1);           // the softmax threads hold S(j) in registers
@@ -232,8 +240,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       AT_TRACE(512, j, 1);
       {
-        const bool okp = mbar_try_wait_nohint(&bars->p_full[0], j & 1);
-        const bool okv = mbar_try_wait_nohint(&bars->v_full[st], ph);
+        const bool okp = mbar_test_wait(&bars->p_full[0], j & 1);
+        const bool okv = mbar_test_wait(&bars->v_full[st], ph);
         if (!okp) mbar_wait_spin(&bars->p_full[0], j & 1);        // P(j) written
         AT_TRACE(512, j, 2);
         if (!okv) mbar_wait_spin(&bars->v_full[st], ph);
@@ -253,8 +261,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       {
         const bool need_v = j + 1 < n_kv, need_k = j + 3 < n_kv;
         const uint32_t ph1 = ((j + 1) >> 1) & 1;
-        const bool okve = (need_v && j >= 1) ? mbar_try_wait_nohint(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1) : true;
-        const bool okke = need_k ? mbar_try_wait_nohint(&bars->k_empty[st ^ 1], ph1) : true;
+        const bool okve = (need_v && j >= 1) ? mbar_test_wait(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1) : true;
+        const bool okke = need_k ? mbar_test_wait(&bars->k_empty[st ^ 1], ph1) : true;
         if (!okve) mbar_wait_spin(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1);
         if (!okke) mbar_wait_spin(&bars->k_empty[st ^ 1], ph1);
         if (elect_one()) {
@@ -277,15 +285,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 24), row sum
     long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 32) ? trace : nullptr;
+    bool s_ready = false;                                         // S(j) already seen complete by the previous step
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
-      mbar_wait_spin(&bars->s_full[0], j & 1);
+      if (!s_ready) mbar_wait_spin(&bars->s_full[0], j & 1);
       tc_fence_after();
       AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off;
-      if (nvalid >= AT_KV) softmax_tile<false>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, bars, m_used, l, tr);
-      else softmax_tile<true>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, bars, m_used, l, tr);
+      if (nvalid >= AT_KV) softmax_tile<false, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, n_kv, bars, m_used, l, s_ready, tr);
+      else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
       AT_TRACE(0, j, 5);
       tc_fence_before();
       mbar_arrive(&bars->p_full[0]);
@@ -347,7 +356,8 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
                            int n_head, cudaStream_t st, long long* trace) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -369,7 +379,8 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   }
   const int q_tiles = (T + 127) / 128;
   const float c_log2 = 0.125f * 1.4426950408889634f;
-  attn_tc_kernel<<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, trace);
+  if (trace) attn_tc_kernel<true><<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, trace);
+  else attn_tc_kernel<false><<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, nullptr);
   return cudaGetLastError();
 }
 

@@ -75,6 +75,19 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
+// non-blocking phase check (try_wait suspends the warp for a hardware time limit when the phase is still open; test_wait
+// returns at once) - used to issue several checks back to back before falling into a wait
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // latency-critical hand-offs: poll without the suspend hint (wake-up from the hinted sleep costs ~a microsecond)
 __device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
