@@ -2,17 +2,21 @@
 // Reference semantics: model.py:92-107 — softmax((q*s)(k*s)^T) v with s = 64^-0.25, softmax in fp32; the
 // [B, H, T, T] score tensor the reference materialises is never written here.
 //
-// One CTA per (clip, head, 128-query tile), KV tiles of 64 keys; two CTAs are resident per SM (256 TMEM columns,
-// 96 KB smem each).  The exponentials (MUFU.EX2) are the binding resource of this kernel, so everything else is
-// arranged so that the 4 softmax warps never wait:
-//   warp 0      TMA producer : Q tile once; K tiles [64 keys x 64] and V^T tiles [64 x 64 keys], 3 stages each
-//   warp 1      MMA issuer   : S(j+1) = Q K(j+1)^T (M128 N64 K64) into the OTHER of two S buffers in TMEM before it
-//                              waits for P(j); then O += P(j) V(j) (M128 N64 K64) with P(j) read from smem
-//   warps 2..5  softmax      : thread = query row = TMEM lane.  One tcgen05.ld of the 64 scores (kept in registers),
-//                              row max, P = 2^(S*c - m) with one ex2.approx per element, bf16 P into one of two
-//                              128B-swizzled smem tiles, lazy rescale of O in TMEM, final O / l -> bf16.
-// The softmax is instruction-issue bound (not MUFU bound), so the row sum l is NOT accumulated by the threads: V^T
-// carries a row of ones and the PV MMA (N = 80) produces l as column 64 of O; scale/subtract uses packed FFMA2.
+// One CTA per (clip, head, 128-query tile), KV tiles of 64 keys, five warps, THREE CTAs resident per SM (57 KB smem,
+// 128 + 32 TMEM columns and a 128-register budget each: registers are allocated per SM sub-partition, 15 warps -> 4 per
+// sub-partition).  The exponentials (MUFU.EX2, ~16 per clock per SM) are the binding resource; three co-resident CTAs
+// keep that pipe fed while any one of them waits on the tensor core.
+//   warp 0      control : TMA producer AND MMA issuer in one converged warp (the elected lane issues).  Per step j:
+//                         S(j+1) = Q K(j+1)^T (M128 N64 K64, both operands in smem) as soon as the softmax threads hold
+//                         S(j) in registers; prefetch K(j+2) (3 stages) and V^T(j+1) (2 stages); O += P(j) V(j) with the
+//                         A operand P(j) read from TENSOR MEMORY (TS-form tcgen05.mma) and V^T(j) from smem.
+//   warps 1..4  softmax : thread = query row = TMEM lane.  One tcgen05.ld of the 64 scores (kept in registers), row max,
+//                         P = 2^(S*c - m) with one ex2.approx per element (packed FFMA2 / FADD2 around it), bf16 pairs
+//                         kept in the registers S frees and stored to TMEM with one tcgen05.st once PV(j-1) has read
+//                         the previous P: the exponentials of step j overlap PV(j-1).  Lazy rescale of O, final O / l.
+// Shared-memory bandwidth was the hidden limit of the earlier versions (P written to and read back from smem, Q re-read
+// for every 64 keys): an SS-form M128 N64 K16 MMA reads 6 KB of operands for 32 cycles of math.  P in TMEM removes a
+// third of that traffic and the generic->async proxy fence.
 // K tail: 1500 = 23*64 + 28; TMA zero-fills rows >= T and those keys are excluded in the last tile only.
 #include "common.cuh"
 #include "kernels.h"
@@ -24,19 +28,20 @@ namespace wat {
 
 constexpr int AT_THREADS = 160;                // 1 control warp (TMA + MMA issue) + 4 softmax warps
 constexpr int AT_KV = 64;                     // keys per step
-constexpr int AT_NSTAGE = 2;                  // K / V^T pipeline stages
+constexpr int AT_KSTAGE = 2;                  // K pipeline stages
+constexpr int AT_NSTAGE = 2;                  // V^T pipeline stages
 constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
 constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
-constexpr int AT_SMEM = AT_Q_BYTES + AT_NSTAGE * (AT_K_BYTES + AT_V_BYTES) + 1024 + 256;
+constexpr int AT_SMEM = AT_Q_BYTES + AT_KSTAGE * AT_K_BYTES + AT_NSTAGE * AT_V_BYTES + 1024 + 256;
 constexpr float AT_LAZY_LOG2 = 24.0f;         // rescale O only when a row max grows by more than 2^24
 constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)
 constexpr int AT_TMEM_P_COLS = 32;            // P as packed bf16 pairs, a second allocation: 3 x (128 + 32) <= 512 columns per SM
 
 struct AttnBars {
   uint64_t q_full;
-  uint64_t k_full[AT_NSTAGE], k_empty[AT_NSTAGE];
-  uint64_t v_full[AT_NSTAGE], v_empty[AT_NSTAGE];
+  uint64_t k_full[AT_KSTAGE];   // "stage empty" barriers are not needed: the control warp learns that an MMA has read its
+  uint64_t v_full[AT_NSTAGE];   // operands from s_free / p_full, which the softmax threads only signal after that MMA's result
   uint64_t s_full[2];       // S written by the MMA (only [0] is used)
   uint64_t s_free;          // the 128 softmax threads hold S(j) in registers: the MMA warp may overwrite S
   uint64_t p_full[2];       // P buffer written by the 128 softmax threads (and S buffer fully read)
@@ -143,7 +148,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
-  uint8_t* sV = sK + AT_NSTAGE * AT_K_BYTES;
+  uint8_t* sV = sK + AT_KSTAGE * AT_K_BYTES;
   AttnBars* bars = reinterpret_cast<AttnBars*>(sV + AT_NSTAGE * AT_V_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,10 +162,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmVT);
     mbar_init(&bars->q_full, 1);
-    for (int s = 0; s < AT_NSTAGE; ++s) {
-      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
-      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
-    }
+    for (int s = 0; s < AT_KSTAGE; ++s) mbar_init(&bars->k_full[s], 1);
+    for (int s = 0; s < AT_NSTAGE; ++s) mbar_init(&bars->v_full[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); mbar_init(&bars->pv_done[s], 1); }
     mbar_init(&bars->s_free, 128);
     fence_mbar_init();
@@ -205,36 +208,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
       umma_commit(&bars->s_full[0]);
-      umma_commit(&bars->k_empty[0]);
     }
     __syncwarp();
-    if (n_kv > 2) {                                                // K(2) into stage 0 as soon as Q K(0)^T has read it
-      mbar_wait_spin(&bars->k_empty[0], 0);
-      if (elect_one()) {
-        mbar_expect_tx(&bars->k_full[0], AT_K_BYTES);
-        tma_load_3d(sK, &tmK, &bars->k_full[0], D + h * 64, 2 * AT_KV, b);
-      }
-      __syncwarp();
-    }
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       AT_TRACE(512, j, 0);
-      // every barrier check costs ~150 cycles even when the phase is complete, so the checks of each group are issued
-      // back to back (latencies overlap): {k_full, s_free} -> QK(j+1);  {p_full, v_full} -> PV(j);  {v_empty, k_empty} -> TMA
+      // Two hand-overs per step, each one barrier-check group (issued back to back with the non-blocking test_wait: a
+      // check costs ~150 cycles even when its phase is complete) and one issue block:
+      //  1. S(j) sits in registers (s_free)  -> Q K(j+1)^T, and K(j+2) is requested into the stage Q K(j)^T has read
+      //     (it has: the softmax threads signalled s_free(j) after loading its result);
+      //  2. P(j) is in TMEM (p_full)         -> P(j) V(j), and V^T(j+1) is requested into the stage PV(j-1) has read
+      //     (it has: the softmax threads stored P(j) only after pv_done(j-1)).
       if (j + 1 < n_kv) {
-        const bool okk = mbar_test_wait(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        const uint32_t phk = ((j + 1) >> 1) & 1;
+        const bool okk = mbar_test_wait(&bars->k_full[st ^ 1], phk);
         const bool oks = mbar_test_wait(&bars->s_free, j & 1);
-        if (!okk) mbar_wait_spin(&bars->k_full[st ^ 1], ((j + 1) >> 1) & 1);
+        if (!okk) mbar_wait_spin(&bars->k_full[st ^ 1], phk);
         AT_TRACE(512, j, 5);
-        if (!oks) mbar_wait_spin(&bars->s_free, j & 1);           // the softmax threads hold S(j) in registers
+        if (!oks) mbar_wait_spin(&bars->s_free, j & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + (st ^ 1) * AT_K_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
           umma_commit(&bars->s_full[0]);
-          umma_commit(&bars->k_empty[st ^ 1]);
+          if (j + 2 < n_kv) {
+            mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
+            tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, (j + 2) * AT_KV, b);
+          }
         }
         __syncwarp();
       }
@@ -242,7 +244,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       {
         const bool okp = mbar_test_wait(&bars->p_full[0], j & 1);
         const bool okv = mbar_test_wait(&bars->v_full[st], ph);
-        if (!okp) mbar_wait_spin(&bars->p_full[0], j & 1);        // P(j) written
+        if (!okp) mbar_wait_spin(&bars->p_full[0], j & 1);
         AT_TRACE(512, j, 2);
         if (!okv) mbar_wait_spin(&bars->v_full[st], ph);
       }
@@ -252,31 +254,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_O, tmem_P + 8 * k, dV + 2 * k, idesc, (j | k) != 0);
-        umma_commit(&bars->v_empty[st]);
         umma_commit(&bars->pv_done[0]);
+        if (j + 1 < n_kv) {
+          mbar_expect_tx(&bars->v_full[st ^ 1], AT_V_BYTES);
+          tma_load_2d(sV + (st ^ 1) * AT_V_BYTES, &tmVT, &bars->v_full[st ^ 1], (j + 1) * AT_KV, bh * VT_ROWS);
+        }
       }
       __syncwarp();
-      // prefetches, off the softmax's critical path and a full step ahead of their use (a K tile takes > 1000 cycles
-      // to arrive with three CTAs per SM): V^T(j+1) into the stage PV(j-1) released, K(j+3) into Q K(j+1)^T's
-      {
-        const bool need_v = j + 1 < n_kv, need_k = j + 3 < n_kv;
-        const uint32_t ph1 = ((j + 1) >> 1) & 1;
-        const bool okve = (need_v && j >= 1) ? mbar_test_wait(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1) : true;
-        const bool okke = need_k ? mbar_test_wait(&bars->k_empty[st ^ 1], ph1) : true;
-        if (!okve) mbar_wait_spin(&bars->v_empty[st ^ 1], ((j - 1) >> 1) & 1);
-        if (!okke) mbar_wait_spin(&bars->k_empty[st ^ 1], ph1);
-        if (elect_one()) {
-          if (need_v) {
-            mbar_expect_tx(&bars->v_full[st ^ 1], AT_V_BYTES);
-            tma_load_2d(sV + (st ^ 1) * AT_V_BYTES, &tmVT, &bars->v_full[st ^ 1], (j + 1) * AT_KV, bh * VT_ROWS);
-          }
-          if (need_k) {
-            mbar_expect_tx(&bars->k_full[st ^ 1], AT_K_BYTES);
-            tma_load_3d(sK + (st ^ 1) * AT_K_BYTES, &tmK, &bars->k_full[st ^ 1], D + h * 64, (j + 3) * AT_KV, b);
-          }
-        }
-        __syncwarp();
-      }
       AT_TRACE(512, j, 4);
     }
   } else {
