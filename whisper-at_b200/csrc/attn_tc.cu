@@ -34,6 +34,7 @@ constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
 constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
 constexpr int AT_SMEM = AT_Q_BYTES + AT_KSTAGE * AT_K_BYTES + AT_NSTAGE * AT_V_BYTES + 1024 + 256;
+constexpr int AT_POLY_PAIR = 0;                // which pair (0,2,4,6; -1 = none) of every 8 scores takes the polynomial 2^x
 constexpr float AT_LAZY_LOG2 = 24.0f;         // rescale O only when a row max grows by more than 2^24
 constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)
 constexpr int AT_TMEM_P_COLS = 32;            // P as packed bf16 pairs, a second allocation: 3 x (128 + 32) <= 512 columns per SM
@@ -109,8 +110,14 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
       const float s0 = __uint_as_float(i < 32 ? a[i & 31] : b[i & 31]);
       const float s1 = __uint_as_float(i < 32 ? a[(i + 1) & 31] : b[(i + 1) & 31]);
       const float2 x = __ffma2_rn(make_float2(s0, s1), c2, nm2);  // one FFMA2 for two elements
-      p[e] = ex2_approx(x.x);
-      p[e + 1] = ex2_approx(x.y);
+      if (e == AT_POLY_PAIR) {                                    // one pair in four on the FMA pipe: MUFU is the binding unit
+        const float2 y = ex2_poly2(x);
+        p[e] = y.x;
+        p[e + 1] = y.y;
+      } else {
+        p[e] = ex2_approx(x.x);
+        p[e + 1] = ex2_approx(x.y);
+      }
       if (MASK && i >= nvalid) p[e] = 0.f;
       if (MASK && i + 1 >= nvalid) p[e + 1] = 0.f;
     }
