@@ -126,72 +126,69 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
 
 // LayerNorm of 20 consecutive rows (one pooling window of the encoder) + the 20x average pool of the SAME rows
 // (model.py:171-174: the pooled state of layer l is the mean of x after block l, i.e. of the input of block l+1's
-// first LayerNorm), so the fp32 residual stream is read once for both.  One CTA per window, thread = 4 columns of
-// all 20 rows (kept in registers); row statistics through warp shuffles + smem.
+// first LayerNorm), so the fp32 residual stream is read once for both.  One CTA of 10 warps per window; a warp
+// normalises rows w and w + 10 one after the other with the row held in registers (like layernorm_kernel, which runs
+// at the HBM roofline) and adds them into its own smem partial of the pool; the partials are summed in a fixed order.
 template <typename OutT>
-__global__ void __launch_bounds__(320) layernorm_pool20_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(320, 3) layernorm_pool20_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, int D, OutT* __restrict__ out,
                                                                float* __restrict__ pooled, int layer, int L, int P) {
-  __shared__ float part[20][10];
-  __shared__ float stat[20];
+  extern __shared__ float ln_part[];                      // [10 warps][D]
   const int g = blockIdx.x;                               // window index = b * P + w
   const int b = g / P, w = g - b * P;
-  const int c = threadIdx.x * 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* src = x + (long long)g * 20 * D + c;
-  float4 v[20];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n4 = D >> 7;                                  // float4 per lane per row (D is a multiple of 128, <= 1280)
+  float* mine = ln_part + warp * D;
+  const float inv_d = 1.0f / (float)D;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const long long row = (long long)g * 20 + warp + half * 10;
+    const float* xr = x + row * D;
+    float4 v[10];
+    float s = 0.f;
 #pragma unroll
-  for (int r = 0; r < 20; ++r) v[r] = *reinterpret_cast<const float4*>(src + (long long)r * D);
-  // pooled state: mean over the 20 rows
-  {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 10; ++i)
+      if (i < n4) {
+        v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
 #pragma unroll
-    for (int r = 0; r < 20; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+    for (int i = 0; i < 10; ++i)
+      if (i < n4) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + bb * bb) + (cc * cc + d * d);
+      }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-5f);
+    OutT* o = out + row * D;
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      if (i < n4) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+        y.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+        y.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+        y.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+        store4<OutT>(o + c, y);
+        float4* pm = reinterpret_cast<float4*>(mine + c);
+        if (half == 0) *pm = v[i];
+        else { const float4 p = *pm; *pm = make_float4(p.x + v[i].x, p.y + v[i].y, p.z + v[i].z, p.w + v[i].w); }
+      }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 4; c < D; c += 1280) {
+    float4 a = *reinterpret_cast<const float4*>(ln_part + c);
+#pragma unroll
+    for (int k = 1; k < 10; ++k) {
+      const float4 p = *reinterpret_cast<const float4*>(ln_part + k * D + c);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
     *reinterpret_cast<float4*>(pooled + (((long long)b * L + layer) * P + w) * D + c) =
         make_float4(a.x * 0.05f, a.y * 0.05f, a.z * 0.05f, a.w * 0.05f);
-  }
-  // row means
-#pragma unroll
-  for (int r = 0; r < 20; ++r) {
-    const float s = warp_sum((v[r].x + v[r].y) + (v[r].z + v[r].w));
-    if (lane == 0) part[r][warp] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 20) {
-    float s = 0.f;
-    for (int i = 0; i < nw; ++i) s += part[threadIdx.x][i];
-    stat[threadIdx.x] = s / (float)D;
-  }
-  __syncthreads();
-  float mean[20];
-#pragma unroll
-  for (int r = 0; r < 20; ++r) mean[r] = stat[r];
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 20; ++r) {
-    const float a = v[r].x - mean[r], bb = v[r].y - mean[r], cc = v[r].z - mean[r], d = v[r].w - mean[r];
-    const float q = warp_sum((a * a + bb * bb) + (cc * cc + d * d));
-    if (lane == 0) part[r][warp] = q;
-  }
-  __syncthreads();
-  if (threadIdx.x < 20) {
-    float q = 0.f;
-    for (int i = 0; i < nw; ++i) q += part[threadIdx.x][i];
-    stat[threadIdx.x] = rsqrtf(q / (float)D + 1e-5f);
-  }
-  __syncthreads();
-  const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
-  const float4 bt = *reinterpret_cast<const float4*>(beta + c);
-  OutT* dst = out + (long long)g * 20 * D + c;
-#pragma unroll
-  for (int r = 0; r < 20; ++r) {
-    const float rs = stat[r];
-    float4 y;
-    y.x = (v[r].x - mean[r]) * rs * gm.x + bt.x;
-    y.y = (v[r].y - mean[r]) * rs * gm.y + bt.y;
-    y.z = (v[r].z - mean[r]) * rs * gm.z + bt.z;
-    y.w = (v[r].w - mean[r]) * rs * gm.w + bt.w;
-    store4<OutT>(dst + (long long)r * D, y);
   }
 }
 
@@ -199,9 +196,17 @@ cudaError_t launch_layernorm_pool20(const float* x, const float* gamma, const fl
                                     bool out_bf16, float* pooled, int layer, int L, cudaStream_t st) {
   if ((D & 127) || D > 1280 || T % 20) return cudaErrorInvalidValue;
   const int P = T / 20;
-  const int grid = B * P, block = D / 4;
-  if (out_bf16) layernorm_pool20_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, gamma, beta, D, (__nv_bfloat16*)out, pooled, layer, L, P);
-  else layernorm_pool20_kernel<float><<<grid, block, 0, st>>>(x, gamma, beta, D, (float*)out, pooled, layer, L, P);
+  const int grid = B * P, block = 320;
+  const size_t smem = (size_t)10 * D * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(layernorm_pool20_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 1280 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(layernorm_pool20_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 1280 * 4);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (out_bf16) layernorm_pool20_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(x, gamma, beta, D, (__nv_bfloat16*)out, pooled, layer, L, P);
+  else layernorm_pool20_kernel<float><<<grid, block, smem, st>>>(x, gamma, beta, D, (float*)out, pooled, layer, L, P);
   return cudaGetLastError();
 }
 
