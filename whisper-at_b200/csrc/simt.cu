@@ -355,6 +355,114 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const TIn* __restrict__
   }
 }
 
+// bf16 fast path of the head attention for T <= 32 (decision windows of <= 32 pooled frames; <= 32 encoder layers) and
+// hd % 16 == 0.  One CTA per (sequence, head):
+//   1. S = Q K^T on mma.sync m16n8k16 (bf16 in, fp32 accumulate; a 32x32 padded tile, the contraction split over the 8
+//      warps, fragments loaded straight from global memory - every Q / K element is used exactly once), partial tiles
+//      summed through smem in a fixed order;
+//   2. row softmax in fp32 (warp per row);
+//   3. O = P V in fp32 FMAs: thread = 4 columns x 16 rows, V read once per row half, P broadcast from smem.
+// (The tcgen05 path is reserved for the encoder: these tiles are 25x25 and the whole head attention is ~2% of a step.)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                             __nv_bfloat16* __restrict__ out, int T, int n_head, int hd,
+                                                             float scale2) {
+  __shared__ float Sp[8][32][33];                         // per-warp partial scores; Sp[0] is reused for P
+  const int seq = blockIdx.x, h = blockIdx.y;
+  const int D = n_head * hd;
+  const long long row0 = (long long)seq * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const __nv_bfloat16* qb = qkv + row0 * 3 * D + h * hd;
+  const __nv_bfloat16* kb = qb + D;
+  const __nv_bfloat16* vb = qb + 2 * D;
+  {
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    for (int ks = warp; ks < (hd >> 4); ks += 8) {
+      const int k0 = ks * 16 + tig * 2;
+      uint32_t a[2][4], b[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(qb + (long long)r0 * 3 * D + k0);
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(qb + (long long)r1 * 3 * D + k0);
+        a[mt][0] = r0 < T ? p0[0] : 0u;
+        a[mt][1] = r1 < T ? p1[0] : 0u;
+        a[mt][2] = r0 < T ? p0[4] : 0u;                   // columns + 8
+        a[mt][3] = r1 < T ? p1[4] : 0u;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = nt * 8 + g;
+        const uint32_t* pk = reinterpret_cast<const uint32_t*>(kb + (long long)n * 3 * D + k0);
+        b[nt][0] = n < T ? pk[0] : 0u;
+        b[nt][1] = n < T ? pk[4] : 0u;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], a[mt], b[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = mt * 16 + g, c = nt * 8 + tig * 2;
+        Sp[warp][r][c] = acc[mt][nt][0];
+        Sp[warp][r][c + 1] = acc[mt][nt][1];
+        Sp[warp][r + 8][c] = acc[mt][nt][2];
+        Sp[warp][r + 8][c + 1] = acc[mt][nt][3];
+      }
+  }
+  __syncthreads();
+  for (int i = warp; i < T; i += 8) {                     // row i is only ever touched by this warp from here on
+    float sc = -INFINITY;
+    if (lane < T) {
+      float a = Sp[0][i][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) a += Sp[k][i][lane];
+      sc = a * scale2;
+    }
+    const float mx = warp_max(sc);
+    const float p = lane < T ? expf(sc - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(p);
+    Sp[0][i][lane] = p * inv;
+  }
+  __syncthreads();
+  const int ncg = hd >> 2, halves = (T + 15) >> 4;
+  for (int idx = threadIdx.x; idx < ncg * halves; idx += 256) {
+    const int half = idx / ncg, e = (idx - half * ncg) * 4;
+    const int rbase = half * 16;
+    float4 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < T; ++j) {
+      const float4 v4 = load4(vb + (long long)j * 3 * D + e);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float p = Sp[0][rbase + r][j];
+        acc[r].x = fmaf(p, v4.x, acc[r].x); acc[r].y = fmaf(p, v4.y, acc[r].y);
+        acc[r].z = fmaf(p, v4.z, acc[r].z); acc[r].w = fmaf(p, v4.w, acc[r].w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (rbase + r < T) store4<__nv_bfloat16>(out + (row0 + rbase + r) * D + h * hd + e, acc[r]);
+  }
+}
+
 cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out_bf16, int n_seq, int T, int n_head,
                               int hd, cudaStream_t st) {
   if (n_seq <= 0) return cudaSuccess;
@@ -365,6 +473,10 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
   if (smem > 48 * 1024) {
     cudaFuncSetAttribute(attn_small_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+  }
+  if (in_bf16 && out_bf16 && T <= 32 && (hd & 15) == 0) {
+    attn_small_mma_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2);
+    return cudaGetLastError();
   }
   if (!in_bf16 && !out_bf16)
     attn_small_kernel<float, float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, T, n_head, hd, scale2);
