@@ -377,6 +377,47 @@ __device__ __forceinline__ void gelu_erf_fast8(float* v) {
   }
 }
 
+// GELU (exact-erf form, model.py nn.GELU) of 8 values with NO special-function unit: erf(z) = z * g(z^2) with g a
+// degree-10 polynomial in w = 2 z^2 / 3.3^2 - 1 (|z| clamped to 3.3, where 1 - erf = 3e-6); max |erf error| 2.6e-6
+// evaluated in fp32 Horner form - well inside the bf16 rounding of the tile it produces.  The fc1 epilogue has to emit
+// 6.4 GELUs per clock per SM to keep up with the MMA; the rcp + ex2 form needs 80% of the MUFU pipe for that.
+__device__ __forceinline__ void gelu_erf_poly8(float* v) {
+  float2 x[4], z[4], w[4], g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = make_float2(v[2 * k], v[2 * k + 1]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    z[k] = __fmul2_rn(x[k], make_float2(0.70710678118654752f, 0.70710678118654752f));
+    z[k].x = fminf(fmaxf(z[k].x, -3.3f), 3.3f);
+    z[k].y = fminf(fmaxf(z[k].y, -3.3f), 3.3f);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    w[k] = __ffma2_rn(__fmul2_rn(z[k], z[k]), make_float2(0.18365472910927455f, 0.18365472910927455f), make_float2(-1.0f, -1.0f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) g[k] = __ffma2_rn(w[k], make_float2(0.0036358654f, 0.0036358654f), make_float2(-0.0094728824f, -0.0094728824f));
+#define WAT_GELU_STEP(c)                                                                   \
+  _Pragma("unroll") for (int k = 0; k < 4; ++k) g[k] = __ffma2_rn(g[k], w[k], make_float2(c, c));
+  WAT_GELU_STEP(0.011186507f)
+  WAT_GELU_STEP(-0.017833412f)
+  WAT_GELU_STEP(0.036543522f)
+  WAT_GELU_STEP(-0.059262153f)
+  WAT_GELU_STEP(0.084123492f)
+  WAT_GELU_STEP(-0.11445422f)
+  WAT_GELU_STEP(0.15207067f)
+  WAT_GELU_STEP(-0.21164291f)
+  WAT_GELU_STEP(0.42813563f)
+#undef WAT_GELU_STEP
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 e = __fmul2_rn(g[k], z[k]);                     // erf(x / sqrt 2)
+    const float2 h = __fmul2_rn(x[k], make_float2(0.5f, 0.5f));
+    const float2 o = __ffma2_rn(h, e, h);
+    v[2 * k] = o.x;
+    v[2 * k + 1] = o.y;
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

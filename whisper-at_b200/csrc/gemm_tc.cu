@@ -64,7 +64,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     if (tr2) tr2[0] = clock64();
     if (g.act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) gelu_erf_fast8(v + i);
+      for (int i = 0; i < 32; i += 8) gelu_erf_poly8(v + i);
     }
     if (tr2) tr2[1] = clock64();
 #pragma unroll
@@ -114,7 +114,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
-      if (g.act == 1) gelu_erf_fast8(v);
+      if (g.act == 1) gelu_erf_poly8(v);
       *reinterpret_cast<uint4*>(cp + i) =
           make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
@@ -132,7 +132,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) gelu_erf_fast8(v + i);
+    for (int i = 0; i < 32; i += 8) gelu_erf_poly8(v + i);
   }
   if (false) {
   } else if (g.epi == TC_EPI_QKV) {
