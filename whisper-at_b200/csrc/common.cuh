@@ -377,42 +377,40 @@ __device__ __forceinline__ void gelu_erf_fast8(float* v) {
   }
 }
 
-// GELU (exact-erf form, model.py nn.GELU) of 8 values with NO special-function unit: erf(z) = z * g(z^2) with g a
-// degree-10 polynomial in w = 2 z^2 / 3.3^2 - 1 (|z| clamped to 3.3, where 1 - erf = 3e-6); max |erf error| 2.6e-6
-// evaluated in fp32 Horner form - well inside the bf16 rounding of the tile it produces.  The fc1 epilogue has to emit
-// 6.4 GELUs per clock per SM to keep up with the MMA; the rcp + ex2 form needs 80% of the MUFU pipe for that.
+// GELU (exact-erf form, model.py nn.GELU) of 8 values with NO special-function unit.  With t = clamp(x / (3.3 sqrt 2), -1, 1)
+// (one saturating FFMA, s = sat(x c + 1/2), t = 2 s - 1) and w = 2 t^2 - 1:   0.5 (1 + erf(x / sqrt 2)) = 0.5 + t G(w),
+// G a degree-10 polynomial (|z| = 3.3 is where 1 - erf = 3e-6).  Max |GELU error| 6e-6 in fp32 Horner form - well inside
+// the bf16 rounding of the tile it produces.  8.5 instructions per value, all on the FMA pipe: the fc1 epilogue has to
+// emit 6.4 GELUs per clock per SM to keep up with the MMA, and the rcp + ex2 form needed 80% of the MUFU pipe for that.
 __device__ __forceinline__ void gelu_erf_poly8(float* v) {
-  float2 x[4], z[4], w[4], g[4];
+  float2 x[4], t[4], w[4], g[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) x[k] = make_float2(v[2 * k], v[2 * k + 1]);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    z[k] = __fmul2_rn(x[k], make_float2(0.70710678118654752f, 0.70710678118654752f));
-    z[k].x = fminf(fmaxf(z[k].x, -3.3f), 3.3f);
-    z[k].y = fminf(fmaxf(z[k].y, -3.3f), 3.3f);
+    const float2 s = make_float2(__saturatef(fmaf(x[k].x, 0.10713739108887084f, 0.5f)),
+                                 __saturatef(fmaf(x[k].y, 0.10713739108887084f, 0.5f)));
+    t[k] = __ffma2_rn(s, make_float2(2.0f, 2.0f), make_float2(-1.0f, -1.0f));
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    w[k] = __ffma2_rn(__fmul2_rn(z[k], z[k]), make_float2(0.18365472910927455f, 0.18365472910927455f), make_float2(-1.0f, -1.0f));
+  for (int k = 0; k < 4; ++k) w[k] = __ffma2_rn(__fmul2_rn(t[k], t[k]), make_float2(2.0f, 2.0f), make_float2(-1.0f, -1.0f));
 #pragma unroll
-  for (int k = 0; k < 4; ++k) g[k] = __ffma2_rn(w[k], make_float2(0.0036358654f, 0.0036358654f), make_float2(-0.0094728824f, -0.0094728824f));
+  for (int k = 0; k < 4; ++k) g[k] = __ffma2_rn(w[k], make_float2(0.00599917769f, 0.00599917769f), make_float2(-0.0156302564f, -0.0156302564f));
 #define WAT_GELU_STEP(c)                                                                   \
   _Pragma("unroll") for (int k = 0; k < 4; ++k) g[k] = __ffma2_rn(g[k], w[k], make_float2(c, c));
-  WAT_GELU_STEP(0.011186507f)
-  WAT_GELU_STEP(-0.017833412f)
-  WAT_GELU_STEP(0.036543522f)
-  WAT_GELU_STEP(-0.059262153f)
-  WAT_GELU_STEP(0.084123492f)
-  WAT_GELU_STEP(-0.11445422f)
-  WAT_GELU_STEP(0.15207067f)
-  WAT_GELU_STEP(-0.21164291f)
-  WAT_GELU_STEP(0.42813563f)
+  WAT_GELU_STEP(0.0184577368f)
+  WAT_GELU_STEP(-0.0294251293f)
+  WAT_GELU_STEP(0.0602968112f)
+  WAT_GELU_STEP(-0.0977825522f)
+  WAT_GELU_STEP(0.138803765f)
+  WAT_GELU_STEP(-0.188849464f)
+  WAT_GELU_STEP(0.2509166f)
+  WAT_GELU_STEP(-0.349210799f)
+  WAT_GELU_STEP(0.706423819f)
 #undef WAT_GELU_STEP
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 e = __fmul2_rn(g[k], z[k]);                     // erf(x / sqrt 2)
-    const float2 h = __fmul2_rn(x[k], make_float2(0.5f, 0.5f));
-    const float2 o = __ffma2_rn(h, e, h);
+    const float2 o = __fmul2_rn(x[k], __ffma2_rn(g[k], t[k], make_float2(0.5f, 0.5f)));
     v[2 * k] = o.x;
     v[2 * k + 1] = o.y;
   }
