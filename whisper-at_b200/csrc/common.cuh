@@ -196,8 +196,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Relaxed: the hand-overs it is used for (TMEM accumulator
+// drained) are ordered by tcgen05.fence::before_thread_sync / after_thread_sync; a release at cluster scope compiles to
+// MEMBAR.ALL.GPU + ERRBAR, which makes the arriving thread wait for all of its earlier global stores (the epilogue's
+// output) - ncu showed 17% of the GELU GEMM's stall samples on those three instructions.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
