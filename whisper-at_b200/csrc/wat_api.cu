@@ -95,6 +95,8 @@ struct wat_handle {
   int head_chunk = 1;
   Buf x, x2, xn, qkv, vt, att, hbuf, logspec, clipmax, melT, pooled, lmean, lnout, nvalid, logits, pcm_stage;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                            // wat_tag_host: H2D of PCM pieces, overlapped with the mel kernel
+  cudaEvent_t piece_ev[8] = {};
   int64_t ws_bytes = 0;
   // per-kernel-class timing (wat_profile)
   bool profiling = false;
@@ -434,7 +436,7 @@ int check_ready(wat_handle* h) {
 }
 
 int mel_frames(wat_handle* h, const void* pcm, bool i16, int64_t clip_stride, const int32_t* n_valid_host, int n_samples, int n_pad,
-               int B, int n_frames, cudaStream_t st) {
+               int B, int n_frames, cudaStream_t st, int clip0 = 0) {      // clip0: slot of the first clip in logspec / clipmax
   // frames that can see signal: t <= (n + 199) / 160 ; they all feed the per-clip max (audio.py:155)
   const int n_total_frames = (n_samples + n_pad) / 160;
   if (n_frames > n_total_frames) return fail(WAT_ERR_INVALID, "n_frames %d exceeds the %d frames of the padded signal", n_frames, n_total_frames);
@@ -444,11 +446,11 @@ int mel_frames(wat_handle* h, const void* pcm, bool i16, int64_t clip_stride, co
   if (n_valid_host) {
     for (int i = 0; i < B; ++i)
       if (n_valid_host[i] < 0 || n_valid_host[i] > n_samples) return fail(WAT_ERR_INVALID, "n_valid[%d] out of range", i);
-    CU(cudaMemcpyAsync(h->nvalid.p, n_valid_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
-    nv_dev = (const int*)h->nvalid.p;
+    CU(cudaMemcpyAsync((int*)h->nvalid.p + clip0, n_valid_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    nv_dev = (const int*)h->nvalid.p + clip0;
   }
   KL(h, launch_mel_power(h->mel, pcm, i16, clip_stride, nv_dev, n_samples, n_pad, B, n_scan, n_frames, n_frames,
-                         (float*)h->logspec.p, (float*)h->clipmax.p, st));
+                         (float*)h->logspec.p + (size_t)clip0 * n_frames * h->cfg.n_mels, (float*)h->clipmax.p + clip0, st));
   h->launches++;                                                 // the clip_max fill kernel
   return 0;
 }
@@ -527,6 +529,10 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
       }
     if (cudaMemcpy(h->pos, pos.data(), sizeof(float) * pos.size(), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "pos upload"); break; }
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "stream create"); break; }
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "stream create"); break; }
+    for (int i = 0; i < 8 && !rc; ++i)
+      if (cudaEventCreateWithFlags(&h->piece_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(WAT_ERR_CUDA, "event create");
+    if (rc) break;
   } while (0);
   if (rc) { wat_destroy(h); return rc; }
   *out = h;
@@ -587,6 +593,8 @@ int wat_destroy(wat_handle* h) {
                  &h->pooled, &h->lmean, &h->lnout, &h->nvalid, &h->logits, &h->pcm_stage};
   for (Buf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 8; ++i) if (h->piece_ev[i]) cudaEventDestroy(h->piece_ev[i]);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
   return WAT_OK;
@@ -637,8 +645,11 @@ int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int
   return run_head(h, pooled, B, t_total, t_start, t_len, dw, logits_out, (cudaStream_t)stream);
 }
 
+// piece_ev / piece_clips: wat_tag_host copies the PCM in pieces of piece_clips clips on its copy stream; the mel kernel of a
+// piece waits for that piece's event only, so the H2D of piece p + 1 overlaps the mel of piece p.
 static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
-                    int32_t B, int32_t dw, float* logits_out, cudaStream_t st) {
+                    int32_t B, int32_t dw, float* logits_out, cudaStream_t st, const cudaEvent_t* piece_ev = nullptr,
+                    int piece_clips = 0) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!pcm || !logits_out || B < 1 || n_samples < 1 || n_samples > 480000) return fail(WAT_ERR_INVALID, "bad argument (clips are <= 480000 samples)");
@@ -651,7 +662,18 @@ static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_strid
     const int nb = std::min(cb, B - b0);
     if ((rc = ensure_ws(h, nb))) return rc;
     const void* p0 = reinterpret_cast<const char*>(pcm) + (size_t)b0 * clip_stride * esz;
-    if ((rc = mel_frames(h, p0, i16, clip_stride, n_valid ? n_valid + b0 : nullptr, n_samples, 480000, nb, 3000, st))) return rc;
+    if (!piece_ev) {
+      if ((rc = mel_frames(h, p0, i16, clip_stride, n_valid ? n_valid + b0 : nullptr, n_samples, 480000, nb, 3000, st))) return rc;
+    } else {
+      for (int q0 = 0; q0 < nb;) {
+        const int piece = (b0 + q0) / piece_clips;
+        const int q1 = std::min(nb, (piece + 1) * piece_clips - b0);
+        CU(cudaStreamWaitEvent(st, piece_ev[piece], 0));
+        if ((rc = mel_frames(h, reinterpret_cast<const char*>(p0) + (size_t)q0 * clip_stride * esz, i16, clip_stride,
+                             n_valid ? n_valid + b0 + q0 : nullptr, n_samples, 480000, q1 - q0, 3000, st, q0))) return rc;
+        q0 = q1;
+      }
+    }
     KL(h, launch_mel_norm((const float*)h->logspec.p, (const float*)h->clipmax.p, nb, 3000, 3000, h->cfg.n_mels, h->bf16 ? 2 : 1,
                           h->melT.p, st));
     if ((rc = run_encoder(h, nb, (float*)h->pooled.p, nullptr, st))) return rc;
@@ -672,8 +694,19 @@ static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t 
   const size_t pcm_bytes = (i16 ? sizeof(int16_t) : sizeof(float)) * ((size_t)(B - 1) * clip_stride + n_samples);
   if ((rc = grow(h, h->pcm_stage, pcm_bytes))) return rc;
   if ((rc = grow(h, h->logits, sizeof(float) * (size_t)B * S * h->cfg.n_class))) return rc;
-  CU(cudaMemcpyAsync(h->pcm_stage.p, pcm_host, pcm_bytes, cudaMemcpyHostToDevice, st));
-  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st))) return rc;
+  // H2D in up to 8 pieces on the copy stream (the previous call ended with a stream synchronize, so the stage is free)
+  const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
+  const int n_piece = B >= 16 ? 8 : 1;
+  const int piece_clips = (B + n_piece - 1) / n_piece;
+  for (int p = 0; p < n_piece; ++p) {
+    const int c0 = p * piece_clips, c1 = std::min(B, c0 + piece_clips);
+    if (c0 >= c1) { CU(cudaEventRecord(h->piece_ev[p], h->copy_stream)); continue; }
+    const size_t off = (size_t)c0 * clip_stride * esz;
+    const size_t bytes = esz * ((size_t)(c1 - c0 - 1) * clip_stride + n_samples);
+    CU(cudaMemcpyAsync((char*)h->pcm_stage.p + off, (const char*)pcm_host + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->piece_ev[p], h->copy_stream));
+  }
+  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st, h->piece_ev, piece_clips))) return rc;
   CU(cudaMemcpyAsync(logits_host, h->logits.p, sizeof(float) * (size_t)B * S * h->cfg.n_class, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return WAT_OK;
