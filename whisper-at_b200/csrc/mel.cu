@@ -32,7 +32,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 }
 
 // grid: (ceil(n_frames/MEL_F), B).  logspec: [B, frames_alloc, n_mels] (frames >= n_store only feed the max)
-__global__ void __launch_bounds__(MEL_THREADS)
+__global__ void __launch_bounds__(MEL_THREADS, 2)
 mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_stride, const int* __restrict__ n_valid_arr,
                  int n_valid_all, int n_pad, int n_frames, int n_store, int frames_alloc, int n_mels,
                  const double2* __restrict__ twiddle,      // [400] (cos, sin)(2 pi j / 400)
@@ -43,8 +43,7 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
                  float* __restrict__ logspec, float* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EO* eo = reinterpret_cast<EO*>(smem_raw);                               // [2 parities][MEL_F][100]
-  double2* tw = reinterpret_cast<double2*>(eo + 2 * MEL_F * 100);         // [400]
-  float* xs = reinterpret_cast<float*>(tw + 400);                         // [MEL_SPAN]
+  float* xs = reinterpret_cast<float*>(eo + 2 * MEL_F * 100);             // [MEL_SPAN]
   float* pw = xs + MEL_SPAN;                                              // [MEL_F][MEL_BINS]
   __shared__ float s_max[MEL_THREADS / 32];
 
@@ -57,7 +56,6 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
   const float* xf = reinterpret_cast<const float*>(pcm) + (long long)clip * clip_stride;
   const short* xi = reinterpret_cast<const short*>(pcm) + (long long)clip * clip_stride;
 
-  for (int i = tid; i < 400; i += MEL_THREADS) tw[i] = twiddle[i];
   const int s0 = t0 * 160 - 200;
   for (int i = tid; i < MEL_SPAN; i += MEL_THREADS) {
     int s = s0 + i;
@@ -100,16 +98,14 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) { re[a][b] = 0.0; im[a][b] = 0.0; }
-    int idx[4] = {0, 0, 0, 0};
+    // twiddles w = e^(2 pi i n k / 400) by an fp64 rotation per step instead of a table gather: a gather over bins that
+    // are 8 apart puts every lane of a warp on the same shared-memory banks (25-way conflicts made this kernel 6x slower
+    // than its DFMA count); 99 rotations accumulate ~1e-14 of error, far below the fp32 inputs.
+    double2 w[4], r[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { r[a] = twiddle[kbase + 2 * a]; w[a] = r[a]; }
     const EO* base = eo + (par * MEL_F + fg * 4) * 100;
     for (int n = 1; n < 100; ++n) {
-      double2 w[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        idx[a] += kbase + 2 * a;
-        if (idx[a] >= 400) idx[a] -= 400;
-        w[a] = tw[idx[a]];
-      }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const EO v = base[b * 100 + n];
@@ -118,6 +114,12 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
           re[a][b] = fma(v.e, w[a].x, re[a][b]);
           im[a][b] = fma(v.o, w[a].y, im[a][b]);
         }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double wx = w[a].x * r[a].x - w[a].y * r[a].y;
+        w[a].y = fma(w[a].x, r[a].y, w[a].y * r[a].x);
+        w[a].x = wx;
       }
     }
 #pragma unroll
@@ -260,7 +262,7 @@ __global__ void mel_to_timemajor_kernel(const float* __restrict__ mel, int T, in
 
 // ------------------------------------------------------------------------------------------ host launchers
 size_t mel_power_smem_bytes() {
-  return sizeof(EO) * 2 * MEL_F * 100 + sizeof(double2) * 400 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
+  return sizeof(EO) * 2 * MEL_F * 100 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
 }
 
 cudaError_t launch_mel_power(const MelTables& tb, const void* pcm, bool pcm_i16, long long clip_stride, const int* n_valid_arr,
