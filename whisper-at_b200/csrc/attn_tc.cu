@@ -34,6 +34,7 @@ constexpr int AT_Q_BYTES = 128 * 64 * 2;      // 16 KB
 constexpr int AT_K_BYTES = AT_KV * 64 * 2;    // 8 KB per stage
 constexpr int AT_V_BYTES = 64 * AT_KV * 2;    // 8 KB per stage
 constexpr int AT_SMEM = AT_Q_BYTES + AT_KSTAGE * AT_K_BYTES + AT_NSTAGE * AT_V_BYTES + 1024 + 256;
+constexpr int AT_SMS = 148;                   // B200; only used to guess which tile follows a CTA on its SM slot
 constexpr int AT_POLY_PAIR = 0;                // which pair (0,2,4,6; -1 = none) of every 8 scores takes the polynomial 2^x
 constexpr float AT_LAZY_LOG2 = 24.0f;         // rescale O only when a row max grows by more than 2^24
 constexpr int AT_TMEM_COLS = 128;             // S: [0,64)  O: [64,128)
@@ -174,6 +175,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); mbar_init(&bars->pv_done[s], 1); }
     mbar_init(&bars->s_free, 128);
     fence_mbar_init();
+    // first loads right away: their latency (the Q tile is always a first touch) overlaps the TMEM allocation and the CTA
+    // barrier below; nobody else touches these barriers before that barrier
+    mbar_expect_tx(&bars->q_full, AT_Q_BYTES);
+    tma_load_3d(sQ, &tmQ, &bars->q_full, h * 64, qt * 128, b);
+    mbar_expect_tx(&bars->k_full[0], AT_K_BYTES);
+    tma_load_3d(sK, &tmK, &bars->k_full[0], D + h * 64, 0, b);
+    mbar_expect_tx(&bars->v_full[0], AT_V_BYTES);
+    tma_load_2d(sV, &tmVT, &bars->v_full[0], 0, bh * VT_ROWS);
+    if (n_kv > 1) {
+      mbar_expect_tx(&bars->k_full[1], AT_K_BYTES);
+      tma_load_3d(sK + AT_K_BYTES, &tmK, &bars->k_full[1], D + h * 64, AT_KV, b);
+    }
+    // and the first boxes of the tile that will follow this CTA on its SM slot (three CTAs per SM) go to L2
+    const int nxt = blockIdx.x + 3 * AT_SMS;
+    if (nxt < (int)gridDim.x) {
+      const int nqt = nxt % q_tiles, nbh = nxt / q_tiles, nh = nbh % n_head, nbb = nbh / n_head;
+      tma_prefetch_l2_3d(&tmQ, nh * 64, nqt * 128, nbb);
+      tma_prefetch_l2_3d(&tmK, D + nh * 64, 0, nbb);
+      tma_prefetch_l2_3d(&tmK, D + nh * 64, AT_KV, nbb);
+      tma_prefetch_l2_2d(&tmVT, 0, nbh * VT_ROWS);
+    }
   }
   if (warp == 1) {
     tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS);
@@ -194,21 +216,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);           // both MMAs are M128 N64
     const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
     long long* tr = (trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? trace : nullptr;
-    if (elect_one()) {
-      mbar_expect_tx(&bars->q_full, AT_Q_BYTES);
-      tma_load_3d(sQ, &tmQ, &bars->q_full, h * 64, qt * 128, b);
-      mbar_expect_tx(&bars->k_full[0], AT_K_BYTES);
-      tma_load_3d(sK, &tmK, &bars->k_full[0], D + h * 64, 0, b);
-      mbar_expect_tx(&bars->v_full[0], AT_V_BYTES);
-      tma_load_2d(sV, &tmVT, &bars->v_full[0], 0, bh * VT_ROWS);
-      if (n_kv > 1) {
-        mbar_expect_tx(&bars->k_full[1], AT_K_BYTES);
-        tma_load_3d(sK + AT_K_BYTES, &tmK, &bars->k_full[1], D + h * 64, AT_KV, b);
-      }
-    }
-    __syncwarp();
-    mbar_wait(&bars->q_full, 0);
-    mbar_wait(&bars->k_full[0], 0);
+    mbar_wait_spin(&bars->q_full, 0);
+    mbar_wait_spin(&bars->k_full[0], 0);
     tc_fence_after();
     if (elect_one()) {
       const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
