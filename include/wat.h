@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WAT_ABI_VERSION 1
+#define WAT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define WAT_API __attribute__((visibility("default")))
@@ -63,6 +63,32 @@ typedef struct wat_config {
   int32_t max_batch;      /* clips processed per internal chunk (workspace is sized for this); 0 = default */
 } wat_config;
 
+/* Head variants of the TL-TR training recipe (src/whisper_at_train/models.py:49-200).  LW_TR / LW_DOWN_TR are the
+ * package's tl_tr / tl_down_tr heads (what wat_create builds); the others are the paper's baselines. */
+enum wat_head_mode {
+  WAT_HEAD_LW_TR = 0,        /* 'lw_tr_{t}_{l}'            time transformer per layer, layer transformer, mlp      models.py:178-187 */
+  WAT_HEAD_LW_DOWN_TR = 1,   /* 'lw_down_tr_{dim}_{t}_{l}' + LN/linear down-projection first                      models.py:190-200 */
+  WAT_HEAD_MEAN_MLP = 2,     /* 'mean_mlp'   mean over layers and time, mlp                                        models.py:113-117 */
+  WAT_HEAD_LAST_MLP = 3,     /* 'last_mlp'   last layer, mean over time, mlp                                       models.py:120-124 */
+  WAT_HEAD_WA_MLP = 4,       /* 'wa_mlp'     mean over time, learned layer weights / their sum, mlp                models.py:127-132 */
+  WAT_HEAD_MEAN_TR = 5,      /* 'mean_tr_{h}' mean over layers, time transformer, mean over time, mlp              models.py:135-140 */
+  WAT_HEAD_LAST_TR = 6,      /* 'last_tr_{h}'                                                                      models.py:143-148 */
+  WAT_HEAD_WA_TR = 7,        /* 'wa_tr_{h}'                                                                        models.py:151-157 */
+  WAT_HEAD_WA_DOWN_TR = 8    /* 'wa_down_tr_{dim}_{h}'                                                             models.py:160-167 */
+};
+
+typedef struct wat_head_config {
+  int32_t rep_dim;        /* d of the pooled encoder states (multiple of 128) */
+  int32_t n_layer;        /* L */
+  int32_t inter_dim;      /* transformer width of the *_down_* modes (multiple of 128); ignored otherwise */
+  int32_t n_class;        /* label_dim */
+  int32_t mode;           /* enum wat_head_mode */
+  int32_t n_time_head;    /* heads of time_tr  (the {t} / {h} of the mode string) */
+  int32_t n_layer_head;   /* heads of layer_tr (the {l} of the mode string); ignored by the baselines */
+  int32_t precision;      /* enum wat_precision */
+  int32_t max_batch;      /* clips per internal chunk; 0 = default */
+} wat_head_config;
+
 WAT_API int wat_abi_version(void);
 WAT_API const char* wat_last_error(void);
 
@@ -90,6 +116,13 @@ WAT_API int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* poole
  * window dw = int(at_time_res * 2.5); logits_out [B, ceil(t_len/dw), n_class] fp32 device. */
 WAT_API int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int32_t t_start, int32_t t_len,
              int32_t dw, float* logits_out, void* stream);
+
+/* A head-only handle for any wat_head_mode: weights by the TLTR module's own state_dict keys ("time_tr.attn.query.weight",
+ * "mlp_layer.1.bias", "layer_weight", ...; an "at_model." or "module." prefix is accepted).  Usable with wat_set_weight /
+ * wat_finalize / wat_tltr / wat_head_forward / wat_destroy only. */
+WAT_API int wat_head_create(const wat_head_config* cfg, wat_handle** out);
+/* TLTR.forward (models.py:108-200): audio_rep [B, n_layer, Tp, rep_dim] fp32 device, Tp <= 128 -> logits_out [B, n_class] */
+WAT_API int wat_head_forward(wat_handle* h, const float* audio_rep, int32_t B, int32_t Tp, float* logits_out, void* stream);
 
 /* fused mel -> encoder -> head for B clips of <= 480000 samples; logits_out [B, ceil(75/dw), n_class] device */
 WAT_API int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,

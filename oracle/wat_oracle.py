@@ -216,6 +216,41 @@ def tltr_head(pooled: torch.Tensor, sd: Dict[str, torch.Tensor], time_resolution
     return x.reshape(B, S, -1)
 
 
+def tltr_variant(audio_rep: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str, dtype=torch.float32) -> torch.Tensor:
+    """TLTR.forward of the training recipe (src/whisper_at_train/models.py:108-200) for every mode string it knows.
+    audio_rep [B, L, T', d]; sd uses the module's own keys ('time_tr.*', 'mlp_layer.*', 'down_layer.*', 'layer_weight').
+    Returns logits [B, label_dim]."""
+    g = lambda k: sd[k].to(dtype)
+    x = audio_rep.to(dtype)
+    B, L = x.shape[0], x.shape[1]
+    mlp = lambda v: _ln(v, g("mlp_layer.0.weight"), g("mlp_layer.0.bias")) @ g("mlp_layer.1.weight").T + g("mlp_layer.1.bias")
+    down = lambda v: _ln(v, g("down_layer.0.weight"), g("down_layer.0.bias")) @ g("down_layer.1.weight").T + g("down_layer.1.bias")
+    wa = lambda v: (v.permute(0, 2, 3, 1) @ g("layer_weight")) / g("layer_weight").sum()          # models.py:152-153
+    parts = mode.split("_")
+    if mode == "mean_mlp":                                                                       # :113-117
+        return mlp(x.mean(dim=1).mean(dim=1))
+    if mode == "last_mlp":                                                                       # :120-124
+        return mlp(x[:, -1].mean(dim=1))
+    if mode == "wa_mlp":                                                                         # :127-132
+        v = x.mean(dim=2).permute(0, 2, 1)
+        return mlp((v @ g("layer_weight")) / g("layer_weight").sum())
+    if mode.startswith("mean_tr"):                                                               # :135-140
+        return mlp(_block(x.mean(dim=1), sd, "time_tr", int(parts[-1])).mean(dim=1))
+    if mode.startswith("last_tr"):                                                               # :143-148
+        return mlp(_block(x[:, -1], sd, "time_tr", int(parts[-1])).mean(dim=1))
+    if mode.startswith("wa_tr"):                                                                 # :151-157
+        return mlp(_block(wa(x), sd, "time_tr", int(parts[-1])).mean(dim=1))
+    if mode.startswith("wa_down_tr"):                                                            # :160-167
+        return mlp(_block(down(wa(x)), sd, "time_tr", int(parts[-1])).mean(dim=1))
+    if mode.startswith("lw_tr") or mode.startswith("lw_down_tr"):                                # :170-200
+        if mode.startswith("lw_down_tr"):
+            x = down(x)
+        v = _block(x.reshape(B * L, x.shape[2], x.shape[3]), sd, "time_tr", int(parts[-2])).mean(dim=1)
+        v = _block(v.reshape(B, L, -1), sd, "layer_tr", int(parts[-1])).mean(dim=1)
+        return mlp(v)
+    raise ValueError(f"unknown TLTR mode {mode!r}")
+
+
 # --------------------------------------------------------------------------- whole path
 def tag(audio: torch.Tensor, sd: Dict[str, torch.Tensor], n_head: int, n_mels: int = 80,
         time_resolution: float = 10, dtype=torch.float32, at_start: int = 0) -> torch.Tensor:

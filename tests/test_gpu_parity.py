@@ -372,3 +372,55 @@ def test_int16_pcm_ingest_is_bit_identical():
     ref = m.tag_batch(as_float.cuda(), at_time_res=10)
     assert torch.equal(m.tag_batch(pcm16.cuda(), at_time_res=10), ref)
     assert torch.equal(m.tag_batch_host(pcm16, at_time_res=10), ref.cpu())
+
+
+# ------------------------------------------------------------------------------------------ TL-TR head variants (§8f row 4)
+def _tltr_cases():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tltr_variants.npz"))
+    out = []
+    for i, c in enumerate(z["cases"]):
+        mode, L, T, d, B = str(c).split("|")
+        out.append((i, mode, int(L), int(T), int(d), int(B), z[f"case{i}"]))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tltr_head_variants_match_reference(precision):
+    """whisper_at.tltr.TLTR (wat_head_create / wat_head_forward) against the logits the reference's own TLTR class
+    produced for every mode string, and against the oracle on the same inputs"""
+    from whisper_at.tltr import TLTR
+    for i, mode, L, T, d, B, ref in _tltr_cases():
+        sd = synth.synth_tltr_state_dict(mode, L, d, 527, seed=1)
+        x = synth.synth_audio_rep(B, L, T, d, seed=7 + i)
+        m = TLTR(label_dim=527, n_layer=L, rep_dim=d, mode=mode, precision=precision, max_batch=4)
+        m.load_state_dict({("module." + k if i % 2 else k): v for k, v in sd.items()})      # DataParallel prefix accepted
+        got = m(x.cuda()).cpu()
+        m.close()
+        assert got.shape == ref.shape
+        err = max_abs(got, ref)
+        if precision == "fp32":
+            assert err < TOL_FP32, (mode, err)
+        else:
+            assert err < TOL_BF16, (mode, err)
+            assert top5_consistent(got, ref, err), mode
+
+
+def test_tltr_head_errors():
+    from whisper_at.tltr import TLTR
+    m = TLTR(527, 4, 384, "wa_mlp", precision="fp32")
+    sd = synth.synth_tltr_state_dict("wa_mlp", 4, 384)
+    with pytest.raises(_lib.WatError, match="Missing key in state_dict: at_model.layer_weight"):
+        m.load_state_dict({k: v for k, v in sd.items() if k != "layer_weight"})
+    with pytest.raises(_lib.WatError, match="Unexpected key"):
+        m.load_state_dict({"layer_tr.attn.key.weight": torch.zeros(384, 384)})
+    m.close()
+    m = TLTR(527, 4, 384, "mean_mlp", precision="fp32")
+    m.load_state_dict(synth.synth_tltr_state_dict("mean_mlp", 4, 384))
+    # a head-only handle has no mel / encoder
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 5, 25, 384))
+    pcm = torch.zeros(1, 16000, device="cuda")
+    out = torch.empty(1, 3, 527, device="cuda")
+    rc = _lib.lib().wat_tag(m._h, C.c_void_p(pcm.data_ptr()), 16000, None, 16000, 1, 25, C.c_void_p(out.data_ptr()), None)
+    assert rc == _lib.WAT_ERR_STATE and b"head-only" in _lib.lib().wat_last_error()
+    m.close()

@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (wat_\w+)", out))
     assert declared <= exported
-    assert L.wat_abi_version() == 1
+    assert L.wat_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
@@ -210,3 +210,22 @@ def test_feature_file_format_matches_reference_loader(tmp_path):
     t = torch.Tensor(z["arr_0"])                                   # the reference loader's next steps
     t = t[:, :25, :] if t.shape[1] >= 25 else torch.nn.functional.pad(t, (0, 0, 0, 25 - t.shape[1]))
     assert tuple(t.shape) == (4, 25, 384)
+
+
+def test_tltr_mode_strings():
+    """mode-string grammar of the training recipe's TLTR class (models.py:56-106)"""
+    from whisper_at.tltr import parse_mode
+    from whisper_at import _lib as L, synth
+    assert parse_mode("mean_mlp", 1280) == (L.HEAD_MODES["mean_mlp"], 1280, 1, 1)
+    assert parse_mode("last_tr_4", 768) == (L.HEAD_MODES["last_tr"], 768, 4, 1)
+    assert parse_mode("wa_down_tr_512_1", 1280) == (L.HEAD_MODES["wa_down_tr"], 512, 1, 1)
+    assert parse_mode("lw_tr_1_8", 1280) == (L.HEAD_MODES["lw_tr"], 1280, 1, 8)
+    assert parse_mode("lw_down_tr_512_1_8", 1280) == (L.HEAD_MODES["lw_down_tr"], 512, 1, 8)
+    with pytest.raises(ValueError):
+        parse_mode("basic", 1280)
+    with pytest.raises(ValueError):
+        parse_mode("mean_tr_x", 1280)
+    # synth's key set for a mode is what the reference module exposes (pinned by strict loading in make_golden_tltr.py)
+    keys = set(synth.tltr_state_shapes("wa_down_tr_256_1", 4, 384))
+    assert {"layer_weight", "down_layer.1.weight", "time_tr.attn.key.weight", "mlp_layer.1.bias"} <= keys
+    assert not any(k.startswith("layer_tr") for k in keys)

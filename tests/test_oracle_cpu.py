@@ -93,3 +93,28 @@ def test_batch_semantics_are_per_clip():
 
 def test_decision_window_arithmetic():
     assert [O.decision_window(r) for r in (10, 2, 0.4, 4, 30, 0.8)] == [25, 5, 1, 10, 75, 2]
+
+
+def _tltr_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "tltr_variants.npz"))
+    for i, c in enumerate(z["cases"]):
+        mode, L, T, d, B = str(c).split("|")
+        yield i, mode, int(L), int(T), int(d), int(B), z[f"case{i}"]
+
+
+def test_oracle_tltr_variants_match_reference_fixtures(golden_dir):
+    """every head of the training recipe's TLTR class (src/whisper_at_train/models.py:108-200; fixtures made from the
+    real class by oracle/make_golden_tltr.py) — the large-v2-sized case is left to WAT_SLOW"""
+    from whisper_at import synth
+    n = 0
+    for i, mode, L, T, d, B, ref in _tltr_cases(golden_dir):
+        if d > 512 and not os.environ.get("WAT_SLOW"):
+            continue
+        sd = synth.synth_tltr_state_dict(mode, L, d, 527, seed=1)
+        x = synth.synth_audio_rep(B, L, T, d, seed=7 + i)
+        with torch.no_grad():
+            got = O.tltr_variant(x, sd, mode)
+        assert got.shape == ref.shape
+        assert float((got - torch.from_numpy(ref)).abs().max()) < 2e-5, mode
+        n += 1
+    assert n >= 9

@@ -68,6 +68,9 @@ cudaError_t launch_im2col_k3(const void* src, bool bf16, int B, int Tin, int C, 
 cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 
 // TL-TR window regroup (model.py:360-367): pooled [B, L, Tp, D] -> rows (b, s, l, tau), zero rows past Tp
+// baseline heads: reduce the layer axis first (kind 0 = mean, 1 = last layer, 2 = weights w[L] / sum(w)); out rows = (b*S + s)*dw + tau
+cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
+                                     int kind, const float* w, float* out, cudaStream_t st);
 cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S,
                                int D, float* out, cudaStream_t st);
 

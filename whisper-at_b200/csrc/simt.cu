@@ -556,6 +556,50 @@ cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, 
   return cudaGetLastError();
 }
 
+// Layer reduction of the baseline heads (models.py:113-167): mean over layers, last layer, or the learned layer weights
+// divided by their sum; rows of a ragged last window are zero like head_gather's.
+__global__ void head_layer_reduce_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
+                                         int S, int D, int kind, const float* __restrict__ w, float* __restrict__ out) {
+  long long r = blockIdx.x;
+  const int tau = (int)(r % dw); r /= dw;
+  const int s = (int)(r % S);
+  const int b = (int)(r / S);
+  const int t = s * dw + tau;
+  float* o = out + (long long)blockIdx.x * D;
+  if (t >= Tp) {
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float* src = pooled + ((long long)b * L * Tp_total + t_start + t) * D;
+  const long long lstride = (long long)Tp_total * D;
+  float wsum = 0.f;
+  if (kind == 2) for (int l = 0; l < L; ++l) wsum += w[l];
+  for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kind == 1) {
+      a = *reinterpret_cast<const float4*>(src + (L - 1) * lstride + e);
+    } else {
+      for (int l = 0; l < L; ++l) {
+        const float4 v = *reinterpret_cast<const float4*>(src + l * lstride + e);
+        const float c = kind == 2 ? w[l] : 1.0f;
+        a.x = fmaf(c, v.x, a.x); a.y = fmaf(c, v.y, a.y); a.z = fmaf(c, v.z, a.z); a.w = fmaf(c, v.w, a.w);
+      }
+      const float inv = kind == 2 ? 1.0f / wsum : 1.0f / (float)L;
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    }
+    *reinterpret_cast<float4*>(o + e) = a;
+  }
+}
+
+cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
+                                     int kind, const float* w, float* out, cudaStream_t st) {
+  const long long rows = (long long)B * S * dw;
+  if (rows <= 0) return cudaSuccess;
+  if (kind == 2 && !w) return cudaErrorInvalidValue;
+  head_layer_reduce_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ im2col (k=3, pad=1)
 __global__ void im2col_k3_kernel(const uint4* __restrict__ src, int Tin, int Cv, int stride, int Tout, uint4* __restrict__ out) {
   const long long row = blockIdx.x;

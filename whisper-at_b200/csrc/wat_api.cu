@@ -87,6 +87,9 @@ struct wat_handle {
   __nv_bfloat16 *conv1_w_h = nullptr, *conv2_w_h = nullptr;
   std::vector<BlockW> enc;
   BlockW time_tr, layer_tr;
+  bool head_only = false;                            // wat_head_create: no mel tables, no encoder
+  int head_mode = WAT_HEAD_LW_TR;
+  float* layer_w = nullptr;                          // 'wa_*' modes: learned layer weights [L]
   float *down_g = nullptr, *down_b = nullptr, *down_w = nullptr, *down_bias = nullptr, *cls_g, *cls_b, *cls_w, *cls_bias;
   __nv_bfloat16* down_w_h = nullptr;
   // workspace (grow-only)
@@ -193,6 +196,31 @@ int make_block(wat_handle* h, BlockW& b, const std::string& p, int D, int H) {
   return 0;
 }
 
+bool head_has_down(int m) { return m == WAT_HEAD_LW_DOWN_TR || m == WAT_HEAD_WA_DOWN_TR; }
+bool head_has_time_tr(int m) { return m != WAT_HEAD_MEAN_MLP && m != WAT_HEAD_LAST_MLP && m != WAT_HEAD_WA_MLP; }
+bool head_has_layer_tr(int m) { return m == WAT_HEAD_LW_TR || m == WAT_HEAD_LW_DOWN_TR; }
+bool head_has_layer_w(int m) { return m == WAT_HEAD_WA_MLP || m == WAT_HEAD_WA_TR || m == WAT_HEAD_WA_DOWN_TR; }
+
+// parameters of the head (ATModel.__init__ model.py:323-349; TLTR.__init__ src/whisper_at_train/models.py:49-106)
+int add_head_slots(wat_handle* h, int n_time_head, int n_layer_head) {
+  const int d = h->d, di = h->di, m = h->head_mode;
+  int rc;
+  if (head_has_down(m)) {
+    if ((rc = add_slot(h, "at_model.down_layer.0.weight", &h->down_g, d))) return rc;
+    if ((rc = add_slot(h, "at_model.down_layer.0.bias", &h->down_b, d))) return rc;
+    if ((rc = add_slot(h, "at_model.down_layer.1.weight", &h->down_w, (int64_t)di * d))) return rc;
+    if ((rc = add_slot(h, "at_model.down_layer.1.bias", &h->down_bias, di))) return rc;
+  }
+  if (head_has_layer_w(m) && (rc = add_slot(h, "at_model.layer_weight", &h->layer_w, h->L))) return rc;
+  if (head_has_time_tr(m) && (rc = make_block(h, h->time_tr, "at_model.time_tr", di, n_time_head))) return rc;
+  if (head_has_layer_tr(m) && (rc = make_block(h, h->layer_tr, "at_model.layer_tr", di, n_layer_head))) return rc;
+  if ((rc = add_slot(h, "at_model.mlp_layer.0.weight", &h->cls_g, di))) return rc;
+  if ((rc = add_slot(h, "at_model.mlp_layer.0.bias", &h->cls_b, di))) return rc;
+  if ((rc = add_slot(h, "at_model.mlp_layer.1.weight", &h->cls_w, (int64_t)h->cfg.n_class * di))) return rc;
+  if ((rc = add_slot(h, "at_model.mlp_layer.1.bias", &h->cls_bias, h->cfg.n_class))) return rc;
+  return 0;
+}
+
 // slaney mel filterbank, restating librosa.filters.mel(sr=16000, n_fft=400, n_mels) (audio.py:96-101)
 double hz_to_mel(double f) {
   const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
@@ -279,9 +307,9 @@ int ensure_ws(wat_handle* h, int B) {
   const int Bc = B < h->cfg.max_batch ? B : h->cfg.max_batch;
   if (Bc <= h->ws_B) return 0;
   const int64_t d = h->d, L = h->L;
-  const int64_t rows_enc = (int64_t)Bc * 1500;
-  const int64_t head_rows_clip = L * 150;                         // S*dw < 75 + dw <= 150 for dw <= 75
-  int64_t hc = rows_enc / head_rows_clip;
+  const int64_t rows_enc = h->head_only ? 0 : (int64_t)Bc * 1500;
+  const int64_t head_rows_clip = L * 150;                         // S*dw < 75 + dw <= 150 for dw <= 75; Tp <= 128 in wat_head_forward
+  int64_t hc = h->head_only ? Bc : rows_enc / head_rows_clip;
   if (hc < 1) hc = 1;
   if (hc > Bc) hc = Bc;
   const int64_t rows_cap = std::max(rows_enc, hc * head_rows_clip);
@@ -293,7 +321,7 @@ int ensure_ws(wat_handle* h, int B) {
   if ((rc = grow(h, h->qkv, es * rows_cap * 3 * d))) return rc;
   if ((rc = grow(h, h->att, es * rows_cap * d))) return rc;
   if ((rc = grow(h, h->hbuf, es * rows_cap * 4 * d))) return rc;
-  if (h->bf16) {
+  if (h->bf16 && !h->head_only) {
     const size_t before = h->vt.bytes;
     if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;
     if (h->vt.bytes != before) {
@@ -301,11 +329,13 @@ int ensure_ws(wat_handle* h, int B) {
       CU(cudaDeviceSynchronize());                                // one-off: later work may run on any stream
     }
   }
-  if ((rc = grow(h, h->logspec, sizeof(float) * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
-  if ((rc = grow(h, h->clipmax, sizeof(float) * Bc))) return rc;
-  if ((rc = grow(h, h->nvalid, sizeof(int) * Bc))) return rc;
-  if ((rc = grow(h, h->melT, es * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
-  if ((rc = grow(h, h->pooled, sizeof(float) * (size_t)Bc * L * 75 * d))) return rc;
+  if (!h->head_only) {
+    if ((rc = grow(h, h->logspec, sizeof(float) * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
+    if ((rc = grow(h, h->clipmax, sizeof(float) * Bc))) return rc;
+    if ((rc = grow(h, h->nvalid, sizeof(int) * Bc))) return rc;
+    if ((rc = grow(h, h->melT, es * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
+    if ((rc = grow(h, h->pooled, sizeof(float) * (size_t)Bc * L * 75 * d))) return rc;
+  }
   if ((rc = grow(h, h->lmean, sizeof(float) * (size_t)hc * 75 * d))) return rc;
   if ((rc = grow(h, h->lnout, sizeof(float) * (size_t)hc * 75 * d))) return rc;
   h->ws_B = Bc;
@@ -394,9 +424,11 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
              cudaStream_t st) {
   const int d = h->d, di = h->di, L = h->L, nc = h->cfg.n_class;
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
-  if (t_len < 1 || t_len > 75 || t_start < 0 || t_start + t_len > t_total) return fail(WAT_ERR_INVALID, "bad pooled slice");
+  if (t_len < 1 || t_len > (h->head_only ? 128 : 75) || t_start < 0 || t_start + t_len > t_total) return fail(WAT_ERR_INVALID, "bad pooled slice");
   const int S = (t_len + dw - 1) / dw;
-  const int64_t rows_clip = (int64_t)S * L * dw;
+  const int mode = h->head_mode;
+  const bool layerwise = head_has_layer_tr(mode);
+  const int64_t rows_clip = (int64_t)S * (layerwise ? L : 1) * dw;
   int hc = (int)(h->rows_cap / rows_clip);
   if (hc < 1) return fail(WAT_ERR_INVALID, "pooled length %d too long for the workspace", t_len);
   if (hc > h->head_chunk) hc = h->head_chunk;
@@ -407,17 +439,26 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
     const int nb = std::min(hc, B - b0);
     const int rows = (int)(nb * rows_clip);
     const float* pin = pooled + (int64_t)b0 * L * t_total * d;
-    if (h->cfg.at_low_compute) {
-      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, x2, st));
+    float* src0 = head_has_down(mode) ? x2 : x;                   // regrouped input; the down-projection lands in x
+    if (layerwise) {
+      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, src0, st));
+    } else {                                                      // baselines: the layer axis is reduced first (models.py:113-167)
+      const int kind = (mode == WAT_HEAD_LAST_MLP || mode == WAT_HEAD_LAST_TR) ? 1 : head_has_layer_w(mode) ? 2 : 0;
+      KL(h, launch_head_layer_reduce(pin, nb, L, t_total, t_start, t_len, dw, S, d, kind, h->layer_w, src0, st));
+    }
+    if (head_has_down(mode)) {
       KL(h, launch_layernorm(x2, h->down_g, h->down_b, rows, d, h->xn.p, h->bf16, st));
       if ((rc = gemm(h, h->xn.p, d, h->down_w, h->down_w_h, h->down_bias, x, di, nullptr, 0, 0, rows, di, d, 0, true, st))) return rc;
-    } else {
-      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, x, st));
     }
-    if ((rc = run_block(h, h->time_tr, x, nb * S * L, dw, false, st))) return rc;
-    KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st));
-    if ((rc = run_block(h, h->layer_tr, x2, nb * S, L, false, st))) return rc;
-    KL(h, launch_group_mean(x2, nb * S, L, di, (float*)h->lmean.p, di, st));
+    if (layerwise) {
+      if ((rc = run_block(h, h->time_tr, x, nb * S * L, dw, false, st))) return rc;
+      KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st));
+      if ((rc = run_block(h, h->layer_tr, x2, nb * S, L, false, st))) return rc;
+      KL(h, launch_group_mean(x2, nb * S, L, di, (float*)h->lmean.p, di, st));
+    } else {
+      if (head_has_time_tr(mode) && (rc = run_block(h, h->time_tr, x, nb * S, dw, false, st))) return rc;
+      KL(h, launch_group_mean(x, nb * S, dw, di, (float*)h->lmean.p, di, st));
+    }
     KL(h, launch_layernorm((const float*)h->lmean.p, h->cls_g, h->cls_b, nb * S, di, h->lnout.p, false, st));
     GemmF32 g;
     g.A = (const float*)h->lnout.p; g.lda = di; g.W = h->cls_w; g.bias = h->cls_bias;
@@ -428,9 +469,10 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
   return 0;
 }
 
-int check_ready(wat_handle* h) {
+int check_ready(wat_handle* h, bool needs_encoder = true) {
   if (!h) return fail(WAT_ERR_INVALID, "null handle");
   if (!h->finalized) return fail(WAT_ERR_STATE, "wat_finalize has not been called");
+  if (needs_encoder && h->head_only) return fail(WAT_ERR_STATE, "head-only handle (wat_head_create): no mel / encoder on it");
   CU(cudaSetDevice(h->device));
   return 0;
 }
@@ -492,7 +534,7 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (h->bf16 && prop.major != 10) { delete h; return fail(WAT_ERR_CUDA, "bf16 mode needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
   int rc = 0;
-  const int d = h->d, nm = cfg->n_mels, di = h->di;
+  const int d = h->d, nm = cfg->n_mels;
   do {
     if ((rc = build_mel_tables(h))) break;
     if ((rc = add_slot(h, "encoder.conv1.weight", &h->conv1_w, (int64_t)d * nm * 3, nm))) break;
@@ -505,18 +547,8 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
     h->enc.resize(h->L);
     for (int l = 0; l < h->L && !rc; ++l) rc = make_block(h, h->enc[l], "encoder.blocks." + std::to_string(l), d, h->H);
     if (rc) break;
-    if (cfg->at_low_compute) {
-      if ((rc = add_slot(h, "at_model.down_layer.0.weight", &h->down_g, d))) break;
-      if ((rc = add_slot(h, "at_model.down_layer.0.bias", &h->down_b, d))) break;
-      if ((rc = add_slot(h, "at_model.down_layer.1.weight", &h->down_w, (int64_t)di * d))) break;
-      if ((rc = add_slot(h, "at_model.down_layer.1.bias", &h->down_bias, di))) break;
-    }
-    if ((rc = make_block(h, h->time_tr, "at_model.time_tr", di, 1))) break;
-    if ((rc = make_block(h, h->layer_tr, "at_model.layer_tr", di, 8))) break;
-    if ((rc = add_slot(h, "at_model.mlp_layer.0.weight", &h->cls_g, di))) break;
-    if ((rc = add_slot(h, "at_model.mlp_layer.0.bias", &h->cls_b, di))) break;
-    if ((rc = add_slot(h, "at_model.mlp_layer.1.weight", &h->cls_w, (int64_t)cfg->n_class * di))) break;
-    if ((rc = add_slot(h, "at_model.mlp_layer.1.bias", &h->cls_bias, cfg->n_class))) break;
+    h->head_mode = cfg->at_low_compute ? WAT_HEAD_LW_DOWN_TR : WAT_HEAD_LW_TR;
+    if ((rc = add_head_slots(h, 1, 8))) break;
     // default positional table (model.py:52-58); callers may overwrite it through wat_set_weight
     std::vector<float> pos((size_t)1500 * d);
     const double inc = std::log(10000.0) / (d / 2 - 1);
@@ -544,7 +576,12 @@ int wat_set_weight(wat_handle* h, const char* key, const float* host_data, int64
   if (h->finalized) return fail(WAT_ERR_STATE, "handle already finalized");
   CU(cudaSetDevice(h->device));
   if (!strncmp(key, "decoder.", 8)) return WAT_OK;                // ASR decoder: not on this path
-  auto it = h->slots.find(key);
+  std::string norm(key);
+  if (h->head_only) {                                             // TLTR's own keys: [module.]time_tr.* -> at_model.time_tr.*
+    if (!norm.compare(0, 7, "module.")) norm.erase(0, 7);
+    if (norm.compare(0, 9, "at_model.")) norm = "at_model." + norm;
+  }
+  auto it = h->slots.find(norm);
   if (it == h->slots.end()) return fail(WAT_ERR_INVALID, "Unexpected key in state_dict: %s", key);
   Slot& s = it->second;
   if (numel != s.numel) return fail(WAT_ERR_INVALID, "size mismatch for %s: expected %lld elements, got %lld", key, (long long)s.numel, (long long)numel);
@@ -572,12 +609,14 @@ int wat_finalize(wat_handle* h) {
   if (h->bf16) {
     int rc;
     const int64_t d = h->d;
-    if ((rc = to_bf16(h, h->conv1_w, &h->conv1_w_h, d * 3 * h->cfg.n_mels))) return rc;
-    if ((rc = to_bf16(h, h->conv2_w, &h->conv2_w_h, d * 3 * d))) return rc;
-    for (auto& b : h->enc) if ((rc = pack_block_bf16(h, b))) return rc;
-    if ((rc = pack_block_bf16(h, h->time_tr))) return rc;
-    if ((rc = pack_block_bf16(h, h->layer_tr))) return rc;
-    if (h->cfg.at_low_compute && (rc = to_bf16(h, h->down_w, &h->down_w_h, (int64_t)h->di * d))) return rc;
+    if (!h->head_only) {
+      if ((rc = to_bf16(h, h->conv1_w, &h->conv1_w_h, d * 3 * h->cfg.n_mels))) return rc;
+      if ((rc = to_bf16(h, h->conv2_w, &h->conv2_w_h, d * 3 * d))) return rc;
+      for (auto& b : h->enc) if ((rc = pack_block_bf16(h, b))) return rc;
+    }
+    if (head_has_time_tr(h->head_mode) && (rc = pack_block_bf16(h, h->time_tr))) return rc;
+    if (head_has_layer_tr(h->head_mode) && (rc = pack_block_bf16(h, h->layer_tr))) return rc;
+    if (head_has_down(h->head_mode) && (rc = to_bf16(h, h->down_w, &h->down_w_h, (int64_t)h->di * d))) return rc;
     CU(cudaDeviceSynchronize());
   }
   h->finalized = true;
@@ -603,6 +642,7 @@ int wat_destroy(wat_handle* h) {
 int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
                int32_t n_pad, int32_t B, int32_t n_frames, int32_t clamp_scope, float* mel_out, void* stream) {
   if (!h) return fail(WAT_ERR_INVALID, "null handle");
+  if (h->head_only) return fail(WAT_ERR_STATE, "head-only handle (wat_head_create): no mel tables on it");
   CU(cudaSetDevice(h->device));
   int rc = 0;
   if (!pcm || !mel_out || B < 1 || n_samples < 1 || n_pad < 0 || n_frames < 1) return fail(WAT_ERR_INVALID, "bad argument");
@@ -637,12 +677,56 @@ int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* pooled_out, f
 
 int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int32_t t_start, int32_t t_len, int32_t dw,
              float* logits_out, void* stream) {
-  int rc = check_ready(h);
+  int rc = check_ready(h, false);
   if (rc) return rc;
   if (!pooled || !logits_out || B < 1) return fail(WAT_ERR_INVALID, "bad argument");
   if ((rc = ensure_ws(h, std::min(B, h->cfg.max_batch)))) return rc;
   h->cur_stream = (cudaStream_t)stream;
   return run_head(h, pooled, B, t_total, t_start, t_len, dw, logits_out, (cudaStream_t)stream);
+}
+
+int wat_head_create(const wat_head_config* cfg, wat_handle** out) {
+  if (!cfg || !out) return fail(WAT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->mode < WAT_HEAD_LW_TR || cfg->mode > WAT_HEAD_WA_DOWN_TR) return fail(WAT_ERR_INVALID, "unknown head mode %d", cfg->mode);
+  if (cfg->rep_dim <= 0 || cfg->rep_dim % 128) return fail(WAT_ERR_INVALID, "rep_dim must be a multiple of 128");
+  if (cfg->n_layer < 1 || cfg->n_layer > 128) return fail(WAT_ERR_INVALID, "bad n_layer");
+  if (cfg->n_class < 1) return fail(WAT_ERR_INVALID, "bad n_class");
+  if (cfg->precision != WAT_FP32 && cfg->precision != WAT_BF16) return fail(WAT_ERR_INVALID, "bad precision");
+  const int di = head_has_down(cfg->mode) ? cfg->inter_dim : cfg->rep_dim;
+  if (di <= 0 || di % 128) return fail(WAT_ERR_INVALID, "inter_dim must be a multiple of 128");
+  const int nt = head_has_time_tr(cfg->mode) ? cfg->n_time_head : 1, nl = head_has_layer_tr(cfg->mode) ? cfg->n_layer_head : 1;
+  if (nt < 1 || nl < 1 || di % nt || di % nl || (di / nt) % 4 || (di / nl) % 4)
+    return fail(WAT_ERR_INVALID, "head counts (%d, %d) must divide the transformer width %d into multiples of 4", nt, nl, di);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(WAT_ERR_CUDA, "no CUDA device: libwat has no CPU fallback");
+  wat_handle* h = new wat_handle();
+  memset(&h->cfg, 0, sizeof(h->cfg));
+  h->cfg.n_mels = 80; h->cfg.n_audio_ctx = 1500; h->cfg.n_audio_state = cfg->rep_dim; h->cfg.n_audio_head = cfg->rep_dim / 64;
+  h->cfg.n_audio_layer = cfg->n_layer; h->cfg.at_low_compute = head_has_down(cfg->mode); h->cfg.at_dim = di;
+  h->cfg.n_class = cfg->n_class; h->cfg.precision = cfg->precision;
+  h->cfg.max_batch = cfg->max_batch > 0 ? cfg->max_batch : 128;
+  h->bf16 = cfg->precision == WAT_BF16;
+  h->d = cfg->rep_dim; h->H = cfg->rep_dim / 64; h->L = cfg->n_layer; h->di = di;
+  h->head_only = true;
+  h->head_mode = cfg->mode;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&h->device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) {
+    delete h;
+    return fail(WAT_ERR_CUDA, "cannot query device");
+  }
+  h->num_sms = prop.multiProcessorCount;
+  if (h->bf16 && prop.major != 10) { delete h; return fail(WAT_ERR_CUDA, "bf16 mode needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); }
+  int rc = add_head_slots(h, nt, nl);
+  if (!rc && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(WAT_ERR_CUDA, "stream create");
+  if (rc) { wat_destroy(h); return rc; }
+  *out = h;
+  return WAT_OK;
+}
+
+int wat_head_forward(wat_handle* h, const float* audio_rep, int32_t B, int32_t Tp, float* logits_out, void* stream) {
+  if (Tp < 1 || Tp > 128) return fail(WAT_ERR_INVALID, "Tp %d out of range [1,128]", Tp);
+  return wat_tltr(h, audio_rep, B, Tp, 0, Tp, Tp, logits_out, stream);      // one window spanning the whole segment
 }
 
 // piece_ev / piece_clips: wat_tag_host copies the PCM in pieces of piece_clips clips on its copy stream; the mel kernel of a

@@ -19,6 +19,16 @@ class WatConfig(C.Structure):
         "n_class", "precision", "max_batch")]
 
 
+class WatHeadConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "rep_dim", "n_layer", "inter_dim", "n_class", "mode", "n_time_head", "n_layer_head", "precision", "max_batch")]
+
+
+# enum wat_head_mode (include/wat.h)
+HEAD_MODES = {"lw_tr": 0, "lw_down_tr": 1, "mean_mlp": 2, "last_mlp": 3, "wa_mlp": 4, "mean_tr": 5, "last_tr": 6,
+              "wa_tr": 7, "wa_down_tr": 8}
+
+
 class WatError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libwat error {code}: {msg}")
@@ -39,6 +49,8 @@ _SIGS = {
     "wat_logmel": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _fp, _vp]),
     "wat_encoder": (C.c_int, [_vp, _fp, _i32, _fp, _fp, _vp]),
     "wat_tltr": (C.c_int, [_vp, _fp, _i32, _i32, _i32, _i32, _i32, _fp, _vp]),
+    "wat_head_create": (C.c_int, [C.POINTER(WatHeadConfig), C.POINTER(_vp)]),
+    "wat_head_forward": (C.c_int, [_vp, _fp, _i32, _i32, _fp, _vp]),
     "wat_tag": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp, _vp]),
     "wat_tag_host": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp]),
     "wat_tag_pcm16": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp, _vp]),

@@ -174,6 +174,60 @@ def synth_state_dict(n_mels: int, d: int, n_layer: int, low: bool, seed: int = 0
     return out
 
 
+def tltr_state_shapes(mode: str, n_layer: int, rep_dim: int, label_dim: int = 527) -> "OrderedDict[str, tuple]":
+    """Parameters of the training recipe's TLTR module for a mode string (src/whisper_at_train/models.py:49-106),
+    under the module's own key names."""
+    parts = mode.split("_")
+    down = "down" in parts
+    di = int(parts[parts.index("tr") + 1]) if down else rep_dim
+    s = OrderedDict()
+    if down:
+        s["down_layer.0.weight"] = (rep_dim,)
+        s["down_layer.0.bias"] = (rep_dim,)
+        s["down_layer.1.weight"] = (di, rep_dim)
+        s["down_layer.1.bias"] = (di,)
+    if parts[0] == "wa":
+        s["layer_weight"] = (n_layer,)
+    if "tr" in parts:
+        s.update(_block_shapes("time_tr", di))
+    if parts[0] == "lw":
+        s.update(_block_shapes("layer_tr", di))
+    s["mlp_layer.0.weight"] = (di,)
+    s["mlp_layer.0.bias"] = (di,)
+    s["mlp_layer.1.weight"] = (label_dim, di)
+    s["mlp_layer.1.bias"] = (label_dim,)
+    return s
+
+
+def synth_tltr_state_dict(mode: str, n_layer: int, rep_dim: int, label_dim: int = 527, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """Seeded 'lively' weights for a TLTR head variant (LN gains U(0.5,1.5), biases N(0,0.1), positive layer weights)."""
+    shapes = tltr_state_shapes(mode, n_layer, rep_dim, label_dim)
+    out: Dict[str, torch.Tensor] = OrderedDict()
+    for name, shape in shapes.items():
+        g = torch.Generator().manual_seed(_seed_for("tltr." + mode + "." + name, seed))
+        if name == "layer_weight":
+            w = 0.2 + torch.rand(shape, generator=g)
+        elif _is_norm(name):
+            w = 0.5 + torch.rand(shape, generator=g) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            w = 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for k in shape[1:]:
+                fan_in *= k
+            w = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        out[name] = w.to(torch.float32).contiguous()
+    return out
+
+
+def synth_audio_rep(batch: int, n_layer: int, t: int, rep_dim: int, seed: int = 7) -> torch.Tensor:
+    """Pooled-encoder-state stand-in [B, L, T', d] for head-only tests: layer-dependent offset and scale."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, n_layer, t, rep_dim, generator=g)
+    scale = 0.5 + torch.arange(n_layer, dtype=torch.float32)[None, :, None, None] / n_layer
+    return (x * scale + 0.1 * torch.randn(1, n_layer, 1, rep_dim, generator=g)).contiguous()
+
+
 def sinusoid_table(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
     """Positional table of the encoder (reference model.py:52-58): cat(sin, cos) of
     t * exp(-ln(max_timescale)/(channels/2-1) * i). Computed with the same fp32 torch ops
