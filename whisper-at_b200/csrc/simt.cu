@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll 2
     for (int ks = warp; ks < (hd >> 4); ks += 8) {
       const int k0 = ks * 16 + tig * 2;
       uint32_t a[2][4], b[4][2];
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16
     float4 acc[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
     for (int j = 0; j < T; ++j) {
       const float4 v4 = load4(vb + (long long)j * 3 * D + e);
 #pragma unroll
