@@ -47,8 +47,26 @@ struct GemmTcDev {
 // `stage` (optional, warp-private 32 x 36 floats): fp32 outputs are transposed through it so that global accesses are
 // 128-byte coalesced (8 lanes x 16 B per row) instead of one 16 B access per row.
 // `bias_chunk`: the 32 bias values of this chunk (global, or the per-tile copy the warp prefetched into smem).
+// the warp's 32 x 32 fp32 residual block in the coalesced (transposed) access pattern of the fp32 epilogue
+__device__ __forceinline__ void load_residual_chunk(const GemmTcDev& g, int row_base, int n0, int lane, float4 (&res)[8]) {
+  const int cc = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row_base + it * 4 + (lane >> 3);
+    res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < g.M && n0 < g.N) {
+      const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
+      res[it] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+    }
+  }
+}
+
+// `res` (optional): the residual block of THIS chunk, loaded by the caller ahead of time; it is refilled with the block at
+// (nxt_row_base, nxt_n0) before this chunk's stores are issued, so a residual read is always one chunk ahead of its use
+// (the residual stream is updated in place, but a chunk's own columns are only read before they are written).
 __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok,
-                                                  const float* bias_chunk, float* stage = nullptr, int lane = 0, long long* tr2 = nullptr) {
+                                                  const float* bias_chunk, float* stage = nullptr, int lane = 0, long long* tr2 = nullptr,
+                                                  float4 (*res_io)[8] = nullptr, int nxt_row_base = -1, int nxt_n0 = 0) {
   if (n0 >= g.N) return;
   if (stage != nullptr && (g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32)) {
     float v[32];
@@ -74,25 +92,20 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     const int cc = (lane & 7) * 4;
     // all residual loads first (R aliases C for the in-place residual stream, so the compiler would otherwise
     // serialise load -> add -> store per row and expose one memory latency per iteration)
-    float4 res[8];
-    if (g.epi == TC_EPI_F32_RES) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int grow = row_base + it * 4 + (lane >> 3);
-        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (grow < g.M) {
-          const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
-          res[it] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
-        }
-      }
-    }
+    float4 res_local[8];
+    float4 (&res)[8] = res_io ? *res_io : res_local;
+    if (g.epi == TC_EPI_F32_RES && !res_io) load_residual_chunk(g, row_base, n0, lane, res);
+    float4 t[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + (lane >> 3);
-      const int grow = row_base + rr;
-      float4 t = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
-      if (g.epi == TC_EPI_F32_RES) { t.x += res[it].x; t.y += res[it].y; t.z += res[it].z; t.w += res[it].w; }
-      if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t;
+      t[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + (lane >> 3)) * 36 + cc);
+      if (g.epi == TC_EPI_F32_RES) { t[it].x += res[it].x; t[it].y += res[it].y; t[it].z += res[it].z; t[it].w += res[it].w; }
+    }
+    if (res_io && nxt_row_base >= 0) load_residual_chunk(g, nxt_row_base, nxt_n0, lane, res);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row_base + it * 4 + (lane >> 3);
+      if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t[it];
     }
     if (tr2) tr2[2] = clock64();
     __syncwarp();
@@ -411,6 +424,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int chalf = (warp - 2) >> 2;                             // which column slice of the tile (COLS wide)
     constexpr int COLS = Cfg2::COLS;
     int it = 0;
+    // fp32 residual epilogue (8 warps): the residual block of a chunk is loaded one chunk (or one tile) ahead of its use
+    const bool res_ahead = EW == 8 && g.epi == TC_EPI_F32_RES;
+    float4 res[8];
+    if (res_ahead && cluster_id < total_tiles)
+      load_residual_chunk(g, (cluster_id / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32, (cluster_id % n_tiles) * BN + chalf * COLS, lane, res);
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
       const int n_blk = tile % n_tiles, m_pair = tile / n_tiles;
       const int as = it & 1;
@@ -423,22 +441,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
-      }
-      // residual epilogues are bound by the latency of the residual read (one exposed HBM round trip per chunk):
-      // pull the NEXT tile's residual block of this warp (32 rows x 128 fp32 columns) into L2 now
-      if (EW == 8 && g.epi == TC_EPI_F32_RES && g.r_mod == 0) {
-        const int ntile = tile + n_clusters;
-        if (ntile < total_tiles) {
-          const int nn = ntile % n_tiles, nm = ntile / n_tiles;
-          const int prow0 = nm * 2 * TC_BM + (int)rank * TC_BM + q * 32;
-          const int pcol = nn * BN + chalf * COLS + (lane & 3) * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int prow = prow0 + i * 8 + (lane >> 2);
-            if (prow < g.M && pcol < g.N)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(g.R + (long long)prow * g.ldr + pcol));
-          }
-        }
       }
       __syncwarp();
       long long* tr = (g.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 24) ? g.trace + it * 8 : nullptr;
@@ -463,7 +465,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         long long* tr2 = (tr && c0 == chalf * COLS + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
         if (tr2) tr2[3] = clock64();
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, EW == 8 ? my_stage : nullptr, lane, tr2);
+        if (res_ahead) {
+          int nrb = -1, nn0 = 0;
+          if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
+          else if (tile + n_clusters < total_tiles) {
+            const int nt = tile + n_clusters;
+            nrb = (nt / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
+            nn0 = (nt % n_tiles) * BN + chalf * COLS;
+          }
+          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, my_stage, lane, tr2, &res, nrb, nn0);
+        } else {
+          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, EW == 8 ? my_stage : nullptr, lane, tr2);
+        }
         if (tr) tr[2 + (c0 - chalf * COLS) / 32] = clock64();
       }
     }
