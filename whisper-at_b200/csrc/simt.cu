@@ -114,11 +114,60 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// same, with the row held in registers (one global read; D a multiple of 128, <= 1280): every load of a row is in
+// flight before the first reduction starts
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int M, int D, OutT* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int n4 = D >> 7;
+  const float* xr = x + (long long)row * D;
+  float4 v[10];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < n4) {
+      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  const float inv_d = 1.0f / (float)D;
+  const float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < n4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-5f);
+  OutT* o = out + (long long)row * D;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    if (i < n4) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+      y.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+      y.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+      y.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+      store4<OutT>(o + c, y);
+    }
+}
+
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int D, void* out,
                              bool out_bf16, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
   if (D & 3) return cudaErrorInvalidValue;
   const int grid = (M + 7) / 8;
+  if ((D & 127) == 0 && D <= 1280) {
+    if (out_bf16) layernorm_reg_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (__nv_bfloat16*)out);
+    else layernorm_reg_kernel<float><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (float*)out);
+    return cudaGetLastError();
+  }
   if (out_bf16) layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (__nv_bfloat16*)out);
   else layernorm_kernel<float><<<grid, 256, 0, st>>>(x, gamma, beta, M, D, (float*)out);
   return cudaGetLastError();
