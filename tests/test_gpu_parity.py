@@ -333,6 +333,20 @@ def test_host_buffer_entry_point_and_launch_counter():
     assert host.shape == (3, 3, 527)
 
 
+def test_host_entry_point_pieces_span_chunks():
+    """wat_tag_host copies the PCM in 8 pieces overlapped with the mel kernel; with 19 clips and 16-clip internal
+    chunks the pieces are ragged (3 clips, the last holds 1) and one of them straddles the chunk boundary"""
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="bf16", max_batch=16)
+    a = synth.synth_batch(19, start=2)
+    nv = np.full(19, 480000, dtype=np.int32)
+    nv[[4, 15, 17]] = [100000, 333333, 16000]
+    dev = m.tag_batch(a.cuda(), at_time_res=10, n_valid=nv).cpu()
+    host = m.tag_batch_host(a.pin_memory(), at_time_res=10, n_valid=nv)
+    assert torch.equal(dev, host)
+    pcm16 = (a.clamp(-1, 1) * 32767).round().to(torch.int16)
+    assert torch.equal(m.tag_batch_host(pcm16, at_time_res=10), m.tag_batch(pcm16.cuda(), at_time_res=10).cpu())
+
+
 def test_permutation_and_chunking_invariance():
     """size-independent properties: clip order and internal chunking (max_batch) do not change any clip's logits"""
     a = synth.synth_batch(5, start=1).cuda()

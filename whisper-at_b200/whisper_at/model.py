@@ -269,7 +269,7 @@ class Whisper(nn.Module):
         return out
 
     def tag_batch_host(self, audio: Tensor, at_time_res=10, out: Optional[Tensor] = None,
-                       precision: Optional[str] = None) -> Tensor:
+                       precision: Optional[str] = None, n_valid: Optional[np.ndarray] = None) -> Tensor:
         """Same through HOST buffers (wat_tag_host): `audio` is a CPU tensor [B, n] (pinned for full
         speed); returns CPU logits.  H2D copy, compute and D2H copy all happen inside the call."""
         eng = self.engine(precision)
@@ -282,9 +282,14 @@ class Whisper(nn.Module):
         if out is None:
             out = torch.empty((B, S, 527), dtype=torch.float32)
         assert out.shape == (B, S, 527) and out.dtype == torch.float32 and out.is_contiguous() and not out.is_cuda
+        nv = None
+        if n_valid is not None:
+            nv_arr = np.ascontiguousarray(n_valid, dtype=np.int32)
+            assert nv_arr.shape == (B,)
+            nv = nv_arr.ctypes.data_as(C.c_void_p)
         with torch.cuda.device(eng.device):
             fn = eng.L.wat_tag_host_pcm16 if i16 else eng.L.wat_tag_host
-            _lib.check(fn(eng.h, a.data_ptr(), n, None, n, B, dw, out.data_ptr()))
+            _lib.check(fn(eng.h, a.data_ptr(), n, nv, n, B, dw, out.data_ptr()))
         return out
 
     def kernel_launches(self) -> int:
