@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int M, int D, OutT* __restrict__ out) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  // rows are walked from the END: the producer GEMM wrote the residual stream front to back, so its last row blocks are
+  // the ones still in L2; and the rows normalised last (the first ones) are what the next GEMM reads first
+  const int row = (gridDim.x - 1 - blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int n4 = D >> 7;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(320, 3) layernorm_pool20_kernel(const float* _
                                                                const float* __restrict__ beta, int D, OutT* __restrict__ out,
                                                                float* __restrict__ pooled, int layer, int L, int P) {
   extern __shared__ float ln_part[];                      // [10 warps][D]
-  const int g = blockIdx.x;                               // window index = b * P + w
+  const int g = gridDim.x - 1 - blockIdx.x;               // window index = b * P + w, walked from the end (see layernorm_reg_kernel)
   const int b = g / P, w = g - b * P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n4 = D >> 7;                                  // float4 per lane per row (D is a multiple of 128, <= 1280)
