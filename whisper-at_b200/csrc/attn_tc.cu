@@ -212,7 +212,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     // Control warp: TMA producer and MMA issuer in one converged warp (only the elected lane issues).  Five warps per CTA
     // keep three CTAs on an SM at <= 4 warps per sub-partition, i.e. a 128-register budget for the softmax warps.
-    // Prefetch distances: K two tiles ahead, V^T one tile ahead, so none of the stage-free waits below ever blocks long.
+    // K(j+2) and V^T(j+1) are requested in the two issue blocks of step j (see the loop), K(0), K(1), V^T(0) and Q above.
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);           // both MMAs are M128 N64
     const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ));
     long long* tr = (trace && blockIdx.x == gridDim.x / 2 && lane == 0) ? trace : nullptr;
@@ -330,16 +330,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_P, AT_TMEM_P_COLS); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
-}
-
-__global__ void vt_init_kernel(__nv_bfloat16* vt, int T, int Tpad) {
-  __nv_bfloat16* row = vt + ((long long)blockIdx.x * VT_ROWS + 64) * Tpad;          // the ones row of this (clip, head)
-  for (int t = threadIdx.x; t < Tpad; t += blockDim.x) row[t] = __float2bfloat16_rn(t < T ? 1.0f : 0.0f);
-}
-
-cudaError_t launch_vt_init(__nv_bfloat16* vt, int BH, int T, int Tpad, cudaStream_t st) {
-  vt_init_kernel<<<BH, 256, 0, st>>>(vt, T, Tpad);
-  return cudaGetLastError();
 }
 
 static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,

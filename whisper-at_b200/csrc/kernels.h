@@ -96,10 +96,10 @@ struct GemmTc {
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------- attn_tc.cu
-// V^T buffer: [B, H, VT_ROWS, Tpad] bf16: rows 0..63 = V transposed (written by the QKV epilogue), row 64 = 1 for
-// keys < T (the PV MMA then also produces the softmax row sum), rows 65..79 and keys >= T = 0.
-constexpr int VT_ROWS = 80;
-cudaError_t launch_vt_init(__nv_bfloat16* vt, int BH, int T, int Tpad, cudaStream_t st);
+// V^T buffer: [B, H, VT_ROWS, Tpad] bf16 = V transposed per head (written by the QKV epilogue; K-major B operand of the
+// PV MMA).  Keys T..Tpad-1 are never written and must stay zero (their P is exactly 0, but 0 * garbage could be NaN):
+// the buffer is zeroed when it is allocated.
+constexpr int VT_ROWS = 64;
 // qk: [B*T, 2D] bf16 (q | k), vt as above, out: [B*T, D] bf16
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
                            int Tpad, int n_head, cudaStream_t st, long long* trace = nullptr);

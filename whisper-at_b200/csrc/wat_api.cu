@@ -153,7 +153,7 @@ int grow(wat_handle* h, Buf& b, size_t bytes, bool zero = false) {
   CU(cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
   h->ws_bytes += (int64_t)bytes;
-  if (zero) CU(cudaMemset(b.p, 0, bytes));
+  if (zero) { CU(cudaMemset(b.p, 0, bytes)); CU(cudaDeviceSynchronize()); }   // one-off; later work may run on any (non-blocking) stream
   return 0;
 }
 
@@ -322,12 +322,7 @@ int ensure_ws(wat_handle* h, int B) {
   if ((rc = grow(h, h->att, es * rows_cap * d))) return rc;
   if ((rc = grow(h, h->hbuf, es * rows_cap * 4 * d))) return rc;
   if (h->bf16 && !h->head_only) {
-    const size_t before = h->vt.bytes;
-    if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;
-    if (h->vt.bytes != before) {
-      KL(h, launch_vt_init((__nv_bfloat16*)h->vt.p, Bc * h->H, 1500, 1536, 0));
-      CU(cudaDeviceSynchronize());                                // one-off: later work may run on any stream
-    }
+    if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;   // zeroed: the 36 padding keys stay 0
   }
   if (!h->head_only) {
     if ((rc = grow(h, h->logspec, sizeof(float) * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
@@ -925,7 +920,6 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
   CU(cudaMalloc(&vt, 2 * (size_t)B * n_head * VT_ROWS * Tpad));
   CU(cudaMalloc(&oh, 2 * rows * D));
   CU(cudaMemsetAsync(vt, 0, 2 * (size_t)B * n_head * VT_ROWS * Tpad, st));
-  CU(launch_vt_init(vt, B * n_head, T, Tpad, st));
   CU(launch_f32_to_bf16(x, xh, rows * D, st));
   CU(launch_f32_to_bf16(wqkv, wh, (int64_t)3 * D * D, st));
   GemmTc g;
