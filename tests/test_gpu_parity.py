@@ -34,7 +34,8 @@ def max_abs(a, ref):
 
 def top5_consistent(ours, ref, err):
     """identical top-5 label sets per window, ignoring swaps across a reference gap smaller than 2*err"""
-    ours, ref = torch.as_tensor(ours).cpu().reshape(-1, 527), torch.as_tensor(ref).cpu().reshape(-1, 527)
+    nc = torch.as_tensor(ref).shape[-1]
+    ours, ref = torch.as_tensor(ours).cpu().reshape(-1, nc), torch.as_tensor(ref).cpu().reshape(-1, nc)
     for o, r in zip(ours, ref):
         so, sr = set(torch.topk(o, 5).indices.tolist()), set(torch.topk(r, 5).indices.tolist())
         if so == sr:
@@ -393,8 +394,8 @@ def _tltr_cases():
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tltr_variants.npz"))
     out = []
     for i, c in enumerate(z["cases"]):
-        mode, L, T, d, B = str(c).split("|")
-        out.append((i, mode, int(L), int(T), int(d), int(B), z[f"case{i}"]))
+        mode, L, T, d, B, nc = str(c).split("|")
+        out.append((i, mode, int(L), int(T), int(d), int(B), int(nc), z[f"case{i}"]))
     return out
 
 
@@ -403,10 +404,10 @@ def test_tltr_head_variants_match_reference(precision):
     """whisper_at.tltr.TLTR (wat_head_create / wat_head_forward) against the logits the reference's own TLTR class
     produced for every mode string, and against the oracle on the same inputs"""
     from whisper_at.tltr import TLTR
-    for i, mode, L, T, d, B, ref in _tltr_cases():
-        sd = synth.synth_tltr_state_dict(mode, L, d, 527, seed=1)
+    for i, mode, L, T, d, B, nc, ref in _tltr_cases():
+        sd = synth.synth_tltr_state_dict(mode, L, d, nc, seed=1)
         x = synth.synth_audio_rep(B, L, T, d, seed=7 + i)
-        m = TLTR(label_dim=527, n_layer=L, rep_dim=d, mode=mode, precision=precision, max_batch=4)
+        m = TLTR(label_dim=nc, n_layer=L, rep_dim=d, mode=mode, precision=precision, max_batch=4)
         m.load_state_dict({("module." + k if i % 2 else k): v for k, v in sd.items()})      # DataParallel prefix accepted
         got = m(x.cuda()).cpu()
         m.close()

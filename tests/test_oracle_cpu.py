@@ -98,8 +98,8 @@ def test_decision_window_arithmetic():
 def _tltr_cases(golden_dir):
     z = np.load(os.path.join(golden_dir, "tltr_variants.npz"))
     for i, c in enumerate(z["cases"]):
-        mode, L, T, d, B = str(c).split("|")
-        yield i, mode, int(L), int(T), int(d), int(B), z[f"case{i}"]
+        mode, L, T, d, B, nc = str(c).split("|")
+        yield i, mode, int(L), int(T), int(d), int(B), int(nc), z[f"case{i}"]
 
 
 def test_oracle_tltr_variants_match_reference_fixtures(golden_dir):
@@ -107,14 +107,14 @@ def test_oracle_tltr_variants_match_reference_fixtures(golden_dir):
     real class by oracle/make_golden_tltr.py) — the large-v2-sized case is left to WAT_SLOW"""
     from whisper_at import synth
     n = 0
-    for i, mode, L, T, d, B, ref in _tltr_cases(golden_dir):
+    for i, mode, L, T, d, B, nc, ref in _tltr_cases(golden_dir):
         if d > 512 and not os.environ.get("WAT_SLOW"):
             continue
-        sd = synth.synth_tltr_state_dict(mode, L, d, 527, seed=1)
+        sd = synth.synth_tltr_state_dict(mode, L, d, nc, seed=1)
         x = synth.synth_audio_rep(B, L, T, d, seed=7 + i)
         with torch.no_grad():
             got = O.tltr_variant(x, sd, mode)
         assert got.shape == ref.shape
         assert float((got - torch.from_numpy(ref)).abs().max()) < 2e-5, mode
         n += 1
-    assert n >= 9
+    assert n >= 10
