@@ -44,10 +44,10 @@ struct AttnBars {
   uint64_t q_full;
   uint64_t k_full[AT_KSTAGE];   // "stage empty" barriers are not needed: the control warp learns that an MMA has read its
   uint64_t v_full[AT_NSTAGE];   // operands from s_free / p_full, which the softmax threads only signal after that MMA's result
-  uint64_t s_full[2];       // S written by the MMA (only [0] is used)
+  uint64_t s_full;          // S(j) written by Q K(j)^T
   uint64_t s_free;          // the 128 softmax threads hold S(j) in registers: the MMA warp may overwrite S
-  uint64_t p_full[2];       // P buffer written by the 128 softmax threads (and S buffer fully read)
-  uint64_t pv_done[2];      // PV(j) finished: P buffer j&1 reusable, O stable
+  uint64_t p_full;          // P(j) stored to TMEM by the 128 softmax threads
+  uint64_t pv_done;         // PV(j) finished: the P tile is reusable, O is stable
   uint32_t tmem_slot, tmem_slot_p;
 };
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   mx *= c_log2;
   const bool need = mx > m_used + AT_LAZY_LOG2;
   if (__any_sync(0xffffffffu, need)) {
-    if (j > 0) { mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1); tc_fence_after(); }   // a rescale touches O: PV(j-1) must be done
+    if (j > 0) { mbar_wait_spin(&bars->pv_done, (j - 1) & 1); tc_fence_after(); }   // a rescale touches O: PV(j-1) must be done
     if (TRACE && tr) tr[j * 8 + 7] = 1;
     const float m_new = need ? mx : m_used;
     const float alpha = ex2_approx(m_used - m_new);              // 1 for rows that keep their reference
@@ -135,9 +135,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   // the single P tile in TMEM is read by PV(j-1): only the store waits for it, the exponentials above overlapped it
   // (the check of S(j+1) is issued with it: an mbarrier check costs ~150 cycles even when the phase is complete)
   {
-    const bool okp = j > 0 ? mbar_test_wait(&bars->pv_done[0], (j - 1) & 1) : true;
-    s_next = j + 1 < n_kv ? mbar_test_wait(&bars->s_full[0], (j + 1) & 1) : true;
-    if (!okp) mbar_wait_spin(&bars->pv_done[0], (j - 1) & 1);
+    const bool okp = j > 0 ? mbar_test_wait(&bars->pv_done, (j - 1) & 1) : true;
+    s_next = j + 1 < n_kv ? mbar_test_wait(&bars->s_full, (j + 1) & 1) : true;
+    if (!okp) mbar_wait_spin(&bars->pv_done, (j - 1) & 1);
     tc_fence_after();
   }
   tmem_st32(tP, pk);
@@ -172,7 +172,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(&bars->q_full, 1);
     for (int s = 0; s < AT_KSTAGE; ++s) mbar_init(&bars->k_full[s], 1);
     for (int s = 0; s < AT_NSTAGE; ++s) mbar_init(&bars->v_full[s], 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128); mbar_init(&bars->pv_done[s], 1); }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->pv_done, 1);
     mbar_init(&bars->s_free, 128);
     fence_mbar_init();
     // first loads right away: their latency (the Q tile is always a first touch) overlaps the TMEM allocation and the CTA
@@ -223,7 +225,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint64_t dK = make_smem_desc_sw128(smem_u32(sK));
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
-      umma_commit(&bars->s_full[0]);
+      umma_commit(&bars->s_full);
     }
     __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
@@ -248,7 +250,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + (st ^ 1) * AT_K_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
-          umma_commit(&bars->s_full[0]);
+          umma_commit(&bars->s_full);
           if (j + 2 < n_kv) {
             mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
             tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, (j + 2) * AT_KV, b);
@@ -258,9 +260,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       AT_TRACE(512, j, 1);
       {
-        const bool okp = mbar_test_wait(&bars->p_full[0], j & 1);
+        const bool okp = mbar_test_wait(&bars->p_full, j & 1);
         const bool okv = mbar_test_wait(&bars->v_full[st], ph);
-        if (!okp) mbar_wait_spin(&bars->p_full[0], j & 1);
+        if (!okp) mbar_wait_spin(&bars->p_full, j & 1);
         AT_TRACE(512, j, 2);
         if (!okv) mbar_wait_spin(&bars->v_full[st], ph);
       }
@@ -270,7 +272,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t dV = make_smem_desc_sw128(smem_u32(sV + st * AT_V_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_O, tmem_P + 8 * k, dV + 2 * k, idesc, (j | k) != 0);
-        umma_commit(&bars->pv_done[0]);
+        umma_commit(&bars->pv_done);
         if (j + 1 < n_kv) {
           mbar_expect_tx(&bars->v_full[st ^ 1], AT_V_BYTES);
           tma_load_2d(sV + (st ^ 1) * AT_V_BYTES, &tmVT, &bars->v_full[st ^ 1], (j + 1) * AT_KV, bh * VT_ROWS);
@@ -288,7 +290,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     bool s_ready = false;                                         // S(j) already seen complete by the previous step
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
-      if (!s_ready) mbar_wait_spin(&bars->s_full[0], j & 1);
+      if (!s_ready) mbar_wait_spin(&bars->s_full, j & 1);
       tc_fence_after();
       AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
@@ -297,10 +299,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
       AT_TRACE(0, j, 5);
       tc_fence_before();
-      mbar_arrive(&bars->p_full[0]);
+      mbar_arrive(&bars->p_full);
       AT_TRACE(0, j, 6);
     }
-    mbar_wait_spin(&bars->pv_done[0], (n_kv - 1) & 1);
+    mbar_wait_spin(&bars->pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const int tq = qt * 128 + r;
     __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;

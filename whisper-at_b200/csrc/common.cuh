@@ -338,59 +338,6 @@ __device__ __forceinline__ float ex2_approx(float x) {           // single MUFU.
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// exact-erf GELU for the bf16 tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| < 5e-7 on gelu, far below
-// bf16 resolution) = 2 MUFU + ~12 FMA-pipe ops instead of erff's ~25 instructions
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * z * z);
-  const float er = copysignf(fmaf(-p, e, 1.0f), x);
-  return 0.5f * x * (1.0f + er);
-}
-
-// Eight exact-erf GELUs with packed f32x2 FMA-pipe instructions (sm_100 FFMA2/FMUL2), same A-S 7.1.26 erf written as
-//   q = 0.5 * poly(t) * 2^(-x^2 / (2 ln 2)) = Phi(-|x|),  gelu(x) = max(x, 0) - |x * q|     (~10 issue slots per element)
-// and laid out stage by stage over four f32x2 pairs, so that every dependent step (rcp -> 5 x FFMA2 -> ... ) has
-// four independent instructions next to each other: issued pair after pair the chain latency (~100 cycles) is exposed.
-__device__ __forceinline__ void gelu_erf_fast8(float* v) {
-  float2 x[4], t[4], p[4], e[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) x[k] = make_float2(v[2 * k], v[2 * k + 1]);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 d = __ffma2_rn(make_float2(fabsf(x[k].x), fabsf(x[k].y)), make_float2(0.23164189f, 0.23164189f), make_float2(1.0f, 1.0f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[k].x) : "f"(d.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[k].y) : "f"(d.y));
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 a = __fmul2_rn(__fmul2_rn(x[k], x[k]), make_float2(-0.72134752044448170f, -0.72134752044448170f));
-    e[k] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = __ffma2_rn(t[k], make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = __ffma2_rn(p[k], t[k], make_float2(1.421413741f, 1.421413741f));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = __ffma2_rn(p[k], t[k], make_float2(-0.284496736f, -0.284496736f));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = __ffma2_rn(p[k], t[k], make_float2(0.254829592f, 0.254829592f));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = __fmul2_rn(__fmul2_rn(p[k], t[k]), make_float2(0.5f, 0.5f));
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 r = __fmul2_rn(x[k], __fmul2_rn(p[k], e[k]));
-    v[2 * k] = fmaxf(x[k].x, 0.f) - fabsf(r.x);
-    v[2 * k + 1] = fmaxf(x[k].y, 0.f) - fabsf(r.y);
-  }
-}
-
 // GELU (exact-erf form, model.py nn.GELU) of 8 values with NO special-function unit.  With t = clamp(x / (3.3 sqrt 2), -1, 1)
 // (one saturating FFMA, s = sat(x c + 1/2), t = 2 s - 1) and w = 2 t^2 - 1:   0.5 (1 + erf(x / sqrt 2)) = 0.5 + t G(w),
 // G a degree-10 polynomial (|z| = 3.3 is where 1 - erf = 3e-6).  Max |GELU error| 6e-6 in fp32 Horner form - well inside
