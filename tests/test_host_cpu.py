@@ -229,3 +229,33 @@ def test_tltr_mode_strings():
     keys = set(synth.tltr_state_shapes("wa_down_tr_256_1", 4, 384))
     assert {"layer_weight", "down_layer.1.weight", "time_tr.attn.key.weight", "mlp_layer.1.bias"} <= keys
     assert not any(k.startswith("layer_tr") for k in keys)
+
+
+def test_bench_flop_model_matches_survey_table():
+    """bench.py's algorithmic FLOPs per clip (the numerator of roofline.achieved) against SURVEY.md §8d's table"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("wat_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for (d, L, n_mels, low, res), enc_g, head_g in [((384, 4, 80, False, 10), 36.9, 1.12), ((512, 6, 80, False, 10), 87.4, 2.97),
+                                                     ((768, 12, 80, True, 10), 344.2, 6.65), ((1024, 24, 80, True, 10), 1138.1, 13.8),
+                                                     ((1280, 32, 128, False, 10), 2273.8, 98.5), ((1280, 32, 80, False, 0.4), 2272.7, 189.0)]:
+        f = bench.flops_per_clip(d, L, n_mels, low, res)
+        assert abs(f["encoder"] / 1e9 - enc_g) < 0.002 * enc_g + 0.06, (d, f["encoder"] / 1e9)
+        assert abs((f["total"] - f["encoder"]) / 1e9 - head_g) < 0.01 * head_g + 0.02, (d, (f["total"] - f["encoder"]) / 1e9)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys"""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    j = json.loads(p.stdout.strip().splitlines()[-1])
+    assert j["impl"] == "reference" and j["unit"] == "audio-s/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["e2e"] == {"value": j["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert "workload" in j["config"] and j["vs_baseline"] is None
