@@ -51,7 +51,7 @@ def peaks():
     if os.path.exists(p):
         j = json.load(open(p))
         return dict(tflops=float(j["bf16_tflops_sustained"]), hbm=float(j["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained)")
-    return dict(tflops=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+    return dict(tflops=1590.0, hbm=6650.0, source="of fallback (B200_PROFILING.md: no MEASURED_PEAKS.json)")
 
 
 class ClockSampler(threading.Thread):
@@ -259,6 +259,13 @@ def main():
                    kernel_profile=prof)
         T = 1500
         per_kind = {"gemm_qkv": 2 * T * 3 * d * d, "gemm_out": 2 * T * d * d, "gemm_fc1": 2 * T * 4 * d * d, "gemm_fc2": 2 * T * 4 * d * d}
+        # DRAM traffic of one launch of each encoder GEMM kind from the committed ncu capture (16 clips per launch, MB:
+        # dram__bytes_read.sum + dram__bytes_write.sum) next to the algorithmic bytes of that launch; `traffic` itself stays
+        # null because `achieved` aggregates every GEMM launch of the step rather than one launch
+        if args.model == "large-v2" and not args.low:
+            out["roofline"]["traffic_ncu_MB_per_launch_16clips"] = dict(
+                source="profiles/r01e_v5_all_kernels.txt", gemm_qkv=203.6, gemm_out=274.0, gemm_fc1=267.8, gemm_fc2=644.1,
+                algorithmic=dict(gemm_qkv=255.6, gemm_out=310.5, gemm_fc1=320.3, gemm_fc2=504.8))
         out["roofline"]["encoder_gemm_tflops"] = {k: (f * L * B / (prof[k]["ms_per_step"] / 1000.0) / 1e12) if prof[k]["ms_per_step"] > 0 else None
                                                   for k, f in per_kind.items()}
         if not args.no_cpu_baseline and world == 1:
