@@ -18,8 +18,10 @@ scaled dot-product attention with softmax, exact-erf GELU, average pooling.
 Parity pinning: the reference's own tests hold no vector for this path, so
 the pin is the reference ITSELF run in the build container: oracle/make_golden.py imports
 /root/reference, checks every function here against it (bit-exact or <=2e-6) and commits
-the reference's outputs as tests/golden/*.npz; tests/test_oracle.py re-checks this file
-against those fixtures wherever it runs.
+the reference's outputs as tests/golden/*.npz; tests/test_oracle_cpu.py re-checks this file
+against those fixtures wherever it runs.  The head variants of the training recipe
+(tltr_variant; src/whisper_at_train/models.py:108-200) are pinned the same way by
+oracle/make_golden_tltr.py against the reference's own TLTR class.
 """
 from __future__ import annotations
 
