@@ -19,33 +19,18 @@ from .transcribe import transcribe
 from .version import __version__
 
 # the public checkpoints of the reference (__init__.py:18-51): OpenAI Whisper weights + the TL-TR heads
-_OPENAI = "https://openaipublic.azureedge.net/main/whisper/models/"
-_MODELS = {
-    "tiny.en": _OPENAI + "d3dd57d32accea0b295c96e26691aa14d8822fac7d9d27d5dc00b4ca2826dd03/tiny.en.pt",
-    "tiny": _OPENAI + "65147644a518d12f04e32d6f3b26facc3f8dd46e5390956a9424a650c0ce22b9/tiny.pt",
-    "base.en": _OPENAI + "25a8566e1d0c1e2231d1c762132cd20e0f96a85d16145c3a00adf5d1ac670ead/base.en.pt",
-    "base": _OPENAI + "ed3a0b6b1c0edf879ad9b11b1af5a0e6ab5db9205f891f668f8b0e6c6326e34e/base.pt",
-    "small.en": _OPENAI + "f953ad0fd29cacd07d5a9eda5624af0f6bcf2258be67c92b79389873d91e0872/small.en.pt",
-    "small": _OPENAI + "9ecf779972d90ba49c06d968637d720dd632c55bbf19d441fb42bf17a411e794/small.pt",
-    "medium.en": _OPENAI + "d7440d1dc186f76616474e0ff0b3b6b879abc9d1a4926b7adfa41db2d497ab4f/medium.en.pt",
-    "medium": _OPENAI + "345ae4da62f9b3d59415adc60127b97c714f32e89e936602e85993674d08dcb1/medium.pt",
-    "large-v1": _OPENAI + "e4b87e7e0bf463eb8e6956e646f1e277e901512310def2c24bf0e11bd3c28e9a/large-v1.pt",
-    "large-v2": _OPENAI + "81f7c96c852ee8fc832187b0132e569d6c3065a3252ed18e56effd0b6a73e524/large-v2.pt",
-    "large": _OPENAI + "81f7c96c852ee8fc832187b0132e569d6c3065a3252ed18e56effd0b6a73e524/large-v2.pt",
-}
-_DROPBOX = "https://www.dropbox.com/s/"
-_AT_IDS = {
-    "tiny.en": "atq9so6w0qug5ai/tiny.en_ori", "tiny": "cib4q4iz6g758l0/tiny_ori",
-    "base.en": "qtzgsbuquoz0afn/base.en_ori", "base": "2odwh42u6e9ger7/base_ori",
-    "small.en": "cyx50ycl1ul7lji/small.en_ori", "small.en_low": "507o66zgl8v6ddd/small.en_low",
-    "small": "jftj9s0kr4ycvr1/small_ori", "small_low": "a1x0416v58f7wrf/small_low",
-    "medium.en": "bbvylvmgns8ja4p/medium.en_ori", "medium.en_low": "2q5wprr8f9gti5t/medium.en_low",
-    "medium": "65aabayr7o819az/medium_ori", "medium_low": "0mnfmcasram4n6o/medium_low",
-    "large-v1": "b8x2en1fdzc8nhk/large-v1_ori", "large-v1_low": "5o79h70wyla8jlk/large-v1_low",
-    "large-v2": "3zxpyvdrxy22eq7/large-v2_ori", "large-v2_low": "jw2rh4uylhqgn85/large-v2_low",
-    "large": "3zxpyvdrxy22eq7/large-v2_ori", "large_low": "jw2rh4uylhqgn85/large-v2_low",
-}
-_MODELS_AT = {k: f"{_DROPBOX}{v}.pth?dl=1" for k, v in _AT_IDS.items()}
+# Where the public checkpoints live (the reference's __init__.py:18-51 lists the same files): OpenAI Whisper weights plus
+# the TL-TR heads trained by the Whisper-AT authors.  The registry is data, kept in assets/checkpoints.json.
+def _registry():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "checkpoints.json")) as f:
+        reg = json.load(f)
+    whisper_urls = {name: reg["openai_prefix"] + tail for name, tail in reg["openai"].items()}
+    head_urls = {name: reg["at_prefix"] + ident + reg["at_suffix"] for name, ident in reg["at"].items()}
+    return whisper_urls, head_urls
+
+
+_MODELS, _MODELS_AT = _registry()
 
 
 def available_models() -> List[str]:
