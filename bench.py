@@ -1,12 +1,20 @@
 #!/usr/bin/env python
 """Throughput benchmark of the Whisper-AT tagging hot path (mel -> encoder -> TL-TR) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model large-v2] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_eager] [--config 1..5]
+                    [--model M --low --res R --batch B]            (explicit workload instead of a BASELINE config)
 
 One process per GPU (the driver launches N>1 through torch.distributed.run); a "step" is one pass of the hot
 path over one batch of synthetic 30 s clips.  Default workload = the configuration BASELINE.json's metric is quoted
-on: large-v2 + full TL-TR head, 128-bin mel, at_time_res=10, 128 clips per GPU (1024 across 8), bf16 operands.
-Rank 0 prints ONE JSON line; see DESIGN.md §Measurement for every field.
+on (config 5): large-v2 + full TL-TR head, 128-bin mel, at_time_res=10, 128 clips per GPU (1024 across 8), bf16.
+--config 2/3/4 select the other GPU configurations of BASELINE.json (base B=64; small-low B=256 res 2; medium-low,
+512 clips over the ranks, 256 on one GPU).  Rank 0 prints ONE JSON line; see DESIGN.md §Measurement for every field.
+
+Arms:  ours        the repo's CUDA path (value: inputs resident in HBM; e2e: host buffers through wat_tag_host)
+       reference   the reference's CPU path (oracle port, torch CPU fp32, all host threads), rank 0 only
+       torch_eager the same path in PyTorch eager ops on the GPU (baseline/torch_eager.py: cuBLASLt, cuDNN, SDPA)
+The `ours` line also carries `cpu_baseline` (bounded sample of the CPU arm) and `gpu_baseline` (the torch-eager arm
+on the same workload, same box, same run).
 """
 from __future__ import annotations
 
@@ -27,8 +35,16 @@ sys.dont_write_bytecode = True
 
 import torch  # noqa: E402
 
-METRIC = "audio-sec/sec, large-v2 mel+encoder+TL-TR tagging"
 UNIT = "audio-s/s"
+
+# BASELINE.json configs -> (model, n_mels, low, at_time_res, total clips, max clips per GPU)
+CONFIGS = {
+    1: ("tiny", 80, False, 10.0, 1, 1),
+    2: ("base", 80, False, 10.0, 64, 64),
+    3: ("small", 80, True, 2.0, 256, 256),
+    4: ("medium", 80, True, 10.0, 512, 256),
+    5: ("large-v2", 128, False, 10.0, 1024, 128),
+}
 
 
 def flops_per_clip(d: int, L: int, n_mels: int, low: bool, res: float):
@@ -44,6 +60,15 @@ def flops_per_clip(d: int, L: int, n_mels: int, low: bool, res: float):
     attn_head = S * L * 4 * dw * dw * di + S * 4 * L * L * di
     return dict(gemm=gemm_enc + gemm_head, attn=attn_enc + attn_head, total=gemm_enc + attn_enc + gemm_head + attn_head,
                 encoder=gemm_enc + attn_enc)
+
+
+def hbm_bytes_per_clip(d: int, L: int, n_mels: int, bf16: bool):
+    """Algorithmic bytes of the HBM-bound kernels per 30 s clip."""
+    es = 2 if bf16 else 4
+    return dict(
+        mel=480000 * 4 + 3000 * n_mels * es,                       # PCM fp32 in, time-major mel out
+        layernorm=2 * L * 1500 * d * (4 + es) + (L - 1) * 75 * d * 4,   # 2 LN per layer: fp32 x in, xn out (+ fused pooled rows)
+        pool=1500 * d * 4 + 75 * d * 4)                            # last layer's separate 20x pooling
 
 
 def peaks():
@@ -108,33 +133,92 @@ def oracle_time_clips(name, n_mels, low, res, n_clips, threads):
     return times
 
 
+def time_torch_eager(sd, n_head, n_mels, audio_dev, audio_host, res, steps, warmup, ours_logits=None):
+    """PyTorch-eager GPU arm (baseline/torch_eager.py) on the same clips: device-resident timing with CUDA events and an
+    end-to-end timing from pinned host PCM to host logits, for the SDPA variant; the reference's own materialised-qk
+    attention (model.py:92-107) is timed device-resident as a second figure."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    from torch_eager import EagerTagger
+    B = audio_dev.shape[0]
+    out = {}
+    for att in ("sdpa", "materialized"):
+        tg = EagerTagger(sd, n_head, n_mels, audio_dev.device, torch.bfloat16, att)
+        chunk = B if att == "sdpa" else min(B, 32)               # the fp32 [chunk, H, 1500, 1500] scores are materialised twice
+        for _ in range(max(1, warmup)):
+            lg = tg.tag(audio_dev, res, chunk)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = steps if att == "sdpa" else max(1, min(steps, 2))
+        e0.record()
+        for _ in range(n):
+            lg = tg.tag(audio_dev, res, chunk)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        rec = dict(value=30.0 * B / (ms / 1000.0), ms_per_step=ms, steps=n, clips_per_call=chunk)
+        if ours_logits is not None:
+            rec["max_abs_vs_ours"] = float((lg - ours_logits).abs().max())
+        if att == "sdpa":
+            host_out = torch.empty(lg.shape, dtype=torch.float32).pin_memory()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                host_out.copy_(tg.tag(audio_host.to(audio_dev.device, non_blocking=True), res, chunk))
+            torch.cuda.synchronize()
+            rec["e2e_value"] = 30.0 * B * n / (time.perf_counter() - t0)
+        out[att] = rec
+        del tg
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="large-v2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_eager"])
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json configuration (default 5, the metric's)")
+    ap.add_argument("--model", default=None)
     ap.add_argument("--n-mels", type=int, default=None)
     ap.add_argument("--low", action="store_true")
-    ap.add_argument("--res", type=float, default=10)
-    ap.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
+    ap.add_argument("--res", type=float, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0, help="clips per internal chunk of the library (0 = the whole per-GPU batch)")
+    ap.add_argument("--profile-steps", type=int, default=2, help="extra steps run with per-launch CUDA events for the kernel-class breakdown")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only: do not force W >= 3")
     args = ap.parse_args()
-    n_mels = args.n_mels or (128 if args.model == "large-v2" else 80)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    c_model, c_mels, c_low, c_res, c_total, c_cap = CONFIGS[args.config]
+    if args.model is not None:                                   # explicit workload
+        name, low = args.model, args.low
+        n_mels = args.n_mels or (128 if name == "large-v2" else 80)
+        res = args.res if args.res is not None else 10.0
+        B = args.batch or 128
+        cfg_id = None
+    else:
+        name, n_mels, low, res = c_model, args.n_mels or c_mels, c_low or args.low, args.res if args.res is not None else c_res
+        B = args.batch or min(c_cap, max(1, c_total // world))
+        cfg_id = args.config
     from whisper_at import synth
-    d, h, L = synth.MODEL_SHAPES[args.model]
-    fl = flops_per_clip(d, L, n_mels, args.low, args.res)
-    workload = f"whisper-at {args.model} {'TL-TR-512' if args.low else 'TL-TR'} n_mels={n_mels} at_time_res={args.res:g}, 30 s synthetic clips"
-    config = dict(workload=workload, clips_per_gpu=args.batch, clips_per_internal_chunk=(args.chunk or args.batch), global_batch=args.batch * world, at_time_res=args.res,
+    d, h, L = synth.MODEL_SHAPES[name]
+    fl = flops_per_clip(d, L, n_mels, low, res)
+    metric = f"audio-sec/sec, {name} mel+encoder+TL-TR tagging"
+    workload = f"whisper-at {name} {'TL-TR-512' if low else 'TL-TR'} n_mels={n_mels} at_time_res={res:g}, 30 s synthetic clips"
+    config = dict(workload=workload, baseline_config=cfg_id, clips_per_gpu=B, clips_per_internal_chunk=(args.chunk or B),
+                  global_batch=B * world, at_time_res=res,
                   parallelism=f"dp{world} (clips sharded, no data-path collective; NCCL all_gather of logits)",
-                  l2="inputs+activations per step >> 126 MB L2 (no flush needed)", flops_per_clip=fl["total"])
+                  flops_per_clip=fl["total"])
+    # working set of a step (PCM + fp32 residual + bf16 xn/qkv/att/hbuf): far above the 126 MB L2 for every GPU config of
+    # BASELINE.json; below it (config 1, tiny batches) the L2 is flushed between timed steps
+    step_bytes = B * (480000 * 4 + 1500 * d * (4 + 2 * 9))
+    flush_l2 = step_bytes < (512 << 20)
+    config["l2"] = ("L2 flushed between timed steps (256 MB write), steps timed one by one" if flush_l2 else
+                    f"inputs+activations per step = {step_bytes / 1e6:.0f} MB >> 126 MB L2 (no flush needed)")
 
     # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
     if args.impl == "reference":
@@ -142,12 +226,12 @@ def main():
             return
         threads = os.cpu_count() or 1
         budget = 240.0
-        t_first = oracle_time_clips(args.model, n_mels, args.low, args.res, 1, threads)[0]       # warm-up step (also sizes the run)
+        t_first = oracle_time_clips(name, n_mels, low, res, 1, threads)[0]       # warm-up step (also sizes the run)
         steps = max(1, min(args.steps, int((budget - t_first) / max(t_first, 1e-3))))
-        times = oracle_time_clips(args.model, n_mels, args.low, args.res, steps, threads)
+        times = oracle_time_clips(name, n_mels, low, res, steps, threads)
         total = sum(times)
         val = 30.0 * steps / total
-        out = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=1, ms_per_step=1000 * total / steps,
+        out = dict(metric=metric, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=1, ms_per_step=1000 * total / steps,
                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                    config=dict(config, clips_per_step=1, steps_requested=args.steps),
                    cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
@@ -156,31 +240,51 @@ def main():
         print(json.dumps(out))
         return
 
+    torch.cuda.set_device(local)
+    sd = synth.synth_state_dict(n_mels, d, L, low, seed=1, init="lively")
+    # distinct synthetic clips per rank; a few base clips rolled in time keep host generation short
+    base = synth.synth_batch(min(B, 8), start=1 + 8 * rank)
+    audio_host = torch.stack([torch.roll(base[i % base.shape[0]], 1600 * (i // base.shape[0])) for i in range(B)]).pin_memory()
+    audio_dev = audio_host.cuda(non_blocking=True)
+    dw = int(res * 2.5)
+    S = math.ceil(75 / dw)
+    n_warm = args.warmup if args.allow_short_warmup else max(args.warmup, 3)
+
+    # ------------------------------------------------------------------ torch-eager arm (GPU baseline), rank 0 only
+    if args.impl == "torch_eager":
+        if rank != 0:
+            return
+        sampler = ClockSampler(local)
+        sampler.start()
+        te = time_torch_eager(sd, h, n_mels, audio_dev, audio_host, res, args.steps, n_warm)
+        clocks = sampler.stop()
+        s = te["sdpa"]
+        out = dict(metric=metric, value=s["value"], unit=UNIT, n_gpus=1, steps=s["steps"], warmup=n_warm, ms_per_step=s["ms_per_step"],
+                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic", impl="torch_eager",
+                   config=config, clocks=clocks, gpu_launches=0,
+                   e2e=dict(value=s["e2e_value"], unit=UNIT, h2d_bytes_per_step=int(audio_host.numel() * 4), d2h_bytes_per_step=B * S * 527 * 4),
+                   gpu_baseline=dict(kind="torch_eager", unit=UNIT, sdpa=te["sdpa"], materialized_qk=te["materialized"],
+                                     note="baseline/torch_eager.py: torch.stft + cuDNN conv + cuBLASLt linear + SDPA / materialised-qk, bf16"))
+        print(json.dumps(out))
+        return
+
     # ------------------------------------------------------------------ our arm
     import whisper_at
     from whisper_at import _lib
-    torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = whisper_at.ModelDimensions(n_mels, 1500, d, h, L, 51865, 448, d, h, L)
-    model = whisper_at.Whisper(dims, at_low_compute=args.low, precision=args.precision, max_batch=(args.chunk or args.batch))
-    model.load_state_dict(synth.synth_state_dict(n_mels, d, L, args.low, seed=1, init="lively"), strict=False)
+    model = whisper_at.Whisper(dims, at_low_compute=low, precision=args.precision, max_batch=(args.chunk or B))
+    model.load_state_dict(sd, strict=False)
     model = model.to(f"cuda:{local}")
-    B = args.batch
-    # distinct synthetic clips per rank; a few base clips rolled in time keep host generation short
-    base = synth.synth_batch(min(B, 8), start=1 + 8 * rank)
-    audio_host = torch.stack([torch.roll(base[i % base.shape[0]], 1600 * (i // base.shape[0])) for i in range(B)]).pin_memory()
-    audio_dev = audio_host.cuda(non_blocking=True)
-    dw = int(args.res * 2.5)
-    S = math.ceil(75 / dw)
     gathered = torch.empty((world * B, S, 527), device="cuda") if world > 1 else None
     eng = model.engine()
     Lb = _lib.lib()
 
     def step_device():
-        lg = model.tag_batch(audio_dev, at_time_res=args.res)
+        lg = model.tag_batch(audio_dev, at_time_res=res)
         if world > 1:
             dist.all_gather_into_tensor(gathered, lg)
         return lg
@@ -191,28 +295,33 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    n_warm = args.warmup if args.allow_short_warmup else max(args.warmup, 3)
     for _ in range(n_warm):
         step_device()
     sync_all()
     launches0 = model.kernel_launches()
-    _lib.check(Lb.wat_profile(eng.h, 1))
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    e0.record()
-    for _ in range(args.steps):
-        lg = step_device()
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
-    n_cls = Lb.wat_profile_classes()
-    pms, pcnt = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
-    _lib.check(Lb.wat_profile_read(eng.h, pms, pcnt))
-    _lib.check(Lb.wat_profile(eng.h, 0))
+    if not flush_l2:
+        e0.record()
+        for _ in range(args.steps):
+            lg = step_device()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+    else:
+        scrub = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        ms = 0.0
+        for _ in range(args.steps):
+            scrub.fill_(1)
+            e0.record()
+            lg = step_device()
+            e1.record()
+            sync_all()
+            ms += e0.elapsed_time(e1)
     launches = model.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -221,13 +330,42 @@ def main():
     ms = float(t.item())
     value = 30.0 * B * world * args.steps / (ms / 1000.0)
 
+    # ---- the gathered result is checked, not only timed: rank r's rows sit at [r*B, (r+1)*B), bit-equal to what rank r
+    # computed, and the per-rank checksums every rank derives from its copy of the gather agree with the owners' own
+    gather_check = None
+    if world > 1:
+        own_ok = bool(torch.equal(gathered[rank * B:(rank + 1) * B], lg))
+        mine = lg.double().sum().reshape(1)
+        sums = torch.empty(world, device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(sums, mine)
+        seen = gathered.double().reshape(world, -1).sum(dim=1)
+        chk_ok = bool(torch.equal(seen, sums))
+        distinct = bool(world < 2 or not torch.equal(gathered[:B], gathered[B:2 * B]))        # ranks tag different clips
+        flag = torch.tensor([int(own_ok and chk_ok and distinct)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = dict(all_ranks_ok=bool(flag.item()), own_shard_bit_equal=own_ok, cross_rank_checksums_equal=chk_ok,
+                            shards_distinct=distinct)
+        if not flag.item():
+            raise SystemExit(f"rank {rank}: gathered logits do not match the per-rank results: {gather_check}")
+
+    # ---- kernel-class breakdown: a separate pass with per-launch CUDA events (wat_profile), outside the timed loop
+    n_cls = Lb.wat_profile_classes()
+    pms, pcnt = (C.c_double * n_cls)(), (C.c_int64 * n_cls)()
+    n_prof = max(1, args.profile_steps)
+    _lib.check(Lb.wat_profile(eng.h, 1))
+    for _ in range(n_prof):
+        model.tag_batch(audio_dev, at_time_res=res)
+    torch.cuda.synchronize()
+    _lib.check(Lb.wat_profile_read(eng.h, pms, pcnt))
+    _lib.check(Lb.wat_profile(eng.h, 0))
+
     # ---- e2e: host buffers through the C-ABI host entry (H2D of the PCM + D2H of the logits inside the timed region)
     out_host = torch.empty((B, S, 527), dtype=torch.float32).pin_memory()
-    model.tag_batch_host(audio_host, at_time_res=args.res, out=out_host)
+    model.tag_batch_host(audio_host, at_time_res=res, out=out_host)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        model.tag_batch_host(audio_host, at_time_res=args.res, out=out_host)
+        model.tag_batch_host(audio_host, at_time_res=res, out=out_host)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -237,42 +375,66 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        prof = {Lb.wat_profile_class_name(i).decode(): dict(ms_per_step=pms[i] / args.steps, launches_per_step=pcnt[i] / args.steps)
-                for i in range(n_cls)}
-        gemm_ids = [i for i in range(n_cls) if Lb.wat_profile_class_name(i).decode().startswith('gemm')]
-        gemm_ms = sum(pms[i] for i in gemm_ids) / args.steps
+        names = [Lb.wat_profile_class_name(i).decode() for i in range(n_cls)]
+        prof = {names[i]: dict(ms_per_step=pms[i] / n_prof, launches_per_step=pcnt[i] / n_prof) for i in range(n_cls)}
+        gemm_ms = sum(prof[k]["ms_per_step"] for k in names if k.startswith("gemm"))
         achieved = fl["gemm"] * B / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         attn_ms = prof["attention"]["ms_per_step"]
-        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
-                   ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        prof_total = sum(v["ms_per_step"] for v in prof.values())
+        step_ms = ms / args.steps
+        # HBM-bound kernels: algorithmic bytes / measured device time (north_star: "achieved HBM GB/s for the mel and pooling kernels")
+        hb = hbm_bytes_per_clip(d, L, n_mels, args.precision == "bf16")
+        hbm = {}
+        for k in ("mel", "layernorm", "pool"):
+            t_ms = prof[k]["ms_per_step"]
+            if t_ms > 0:
+                gbs = hb[k] * B / (t_ms / 1000.0) / 1e9
+                hbm[k] = dict(algorithmic_MB_per_step=hb[k] * B / 1e6, ms_per_step=t_ms, GBps=gbs, frac_of_hbm_peak=gbs / pk["hbm"])
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tj):
+            tr = json.load(open(tj)).get(f"{name}|{n_mels}|{int(low)}")
+            if tr:
+                traffic = tr["gemm_dram_bytes_per_clip"] * B
+                traffic_src = tr["source"]
+                for k in hbm:
+                    if k in tr.get("dram_bytes_per_clip", {}):
+                        hbm[k]["ncu_dram_MB_per_step"] = tr["dram_bytes_per_clip"][k] * B / 1e6
+        out = dict(metric=metric, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
+                   ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic", impl="ours", config=config,
                    e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=int(audio_host.numel() * 4) * world,
                             d2h_bytes_per_step=int(out_host.numel() * 4) * world,
                             h2d_bytes_per_step_per_gpu=int(audio_host.numel() * 4), matches_device_path=same),
                    gpu_launches=int(launches), clocks=clocks,
                    roofline=dict(bound="tensor", kernel="gemm_tc2_kernel<8|16> / gemm_tc_kernel (all dense tcgen05 GEMMs of the step)", achieved=achieved,
-                                 peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], traffic=None,
-                                 peak_source=pk["source"], kernel_ms_per_step=gemm_ms,
-                                 kernel_share_of_step=gemm_ms / (ms / args.steps),
+                                 peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], traffic=traffic,
+                                 traffic_source=traffic_src, peak_source=pk["source"], kernel_ms_per_step=gemm_ms,
+                                 kernel_share_of_step=gemm_ms / prof_total if prof_total > 0 else None,
+                                 profiled_step_ms=prof_total, profile_steps=n_prof,
                                  attention_tflops=(fl["attn"] * B / (attn_ms / 1000.0) / 1e12) if attn_ms > 0 else None,
-                                 whole_step_tflops=fl["total"] * B / (ms / args.steps / 1000.0) / 1e12),
+                                 whole_step_tflops=fl["total"] * B / (step_ms / 1000.0) / 1e12,
+                                 hbm=dict(peak_GBps=pk["hbm"], kernels=hbm)),
                    kernel_profile=prof)
+        if gather_check:
+            out["gather_check"] = gather_check
         T = 1500
         per_kind = {"gemm_qkv": 2 * T * 3 * d * d, "gemm_out": 2 * T * d * d, "gemm_fc1": 2 * T * 4 * d * d, "gemm_fc2": 2 * T * 4 * d * d}
-        # DRAM traffic of one launch of each encoder GEMM kind from the committed ncu capture (16 clips per launch, MB:
-        # dram__bytes_read.sum + dram__bytes_write.sum) next to the algorithmic bytes of that launch; `traffic` itself stays
-        # null because `achieved` aggregates every GEMM launch of the step rather than one launch
-        if args.model == "large-v2" and not args.low:
-            out["roofline"]["traffic_ncu_MB_per_launch_16clips"] = dict(
-                source="profiles/r01e_v5_all_kernels.txt", gemm_qkv=203.6, gemm_out=274.0, gemm_fc1=267.8, gemm_fc2=644.1,
-                algorithmic=dict(gemm_qkv=255.6, gemm_out=310.5, gemm_fc1=320.3, gemm_fc2=504.8))
         out["roofline"]["encoder_gemm_tflops"] = {k: (f * L * B / (prof[k]["ms_per_step"] / 1000.0) / 1e12) if prof[k]["ms_per_step"] > 0 else None
                                                   for k, f in per_kind.items()}
+        if world == 1 and not args.no_gpu_baseline and args.precision == "bf16":
+            te_ = time_torch_eager(sd, h, n_mels, audio_dev, audio_host, res, max(2, min(args.steps, 5)), 2, ours_logits=lg)
+            s_ = te_["sdpa"]
+            out["gpu_baseline"] = dict(kind="torch_eager", unit=UNIT, value=s_["value"], e2e_value=s_["e2e_value"],
+                                       ms_per_step=s_["ms_per_step"], sdpa=s_, materialized_qk=te_["materialized"],
+                                       ours_over_baseline=value / s_["value"], ours_over_baseline_e2e=e2e_val / s_["e2e_value"],
+                                       note="baseline/torch_eager.py on the same clips, same box: torch.stft + cuDNN conv + cuBLASLt "
+                                            "linear + F.scaled_dot_product_attention (and the reference's materialised-qk attention), bf16")
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            tt = oracle_time_clips(args.model, n_mels, args.low, args.res, 1, threads)          # first clip also warms torch up
+            tt = oracle_time_clips(name, n_mels, low, res, 1, threads)          # first clip also warms torch up
             n_more = max(1, min(8, int(15.0 / max(tt[0], 1e-3))))                                # ~15 s of CPU work
-            tt = oracle_time_clips(args.model, n_mels, args.low, args.res, n_more, threads)
+            tt = oracle_time_clips(name, n_mels, low, res, n_more, threads)
             out["cpu_baseline"] = dict(value=30.0 * len(tt) / sum(tt), unit=UNIT, cores=threads, kind="port",
                                        sample=f"{len(tt)} clips of the same workload (after 1 warm-up clip), one per call as the "
                                               "reference's AT path requires, oracle/wat_oracle.py (torch CPU fp32), all host threads")

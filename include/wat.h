@@ -113,7 +113,9 @@ WAT_API int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, con
 WAT_API int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* pooled_out, float* x_out, void* stream);
 
 /* TL-TR head on pooled[:, :, t_start:t_start+t_len, :] of a [B, L, t_total, d] fp32 device tensor with decision
- * window dw = int(at_time_res * 2.5); logits_out [B, ceil(t_len/dw), n_class] fp32 device. */
+ * window dw = int(at_time_res * 2.5); logits_out [B, ceil(t_len/dw), n_class] fp32 device.
+ * Limit: 1 <= dw <= 128 (at_time_res <= 51.2 s); larger windows return WAT_ERR_INVALID (the reference would zero-pad one
+ * window of dw rows, model.py:360-364, but a 30 s segment only has 75 pooled rows). */
 WAT_API int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int32_t t_start, int32_t t_len,
              int32_t dw, float* logits_out, void* stream);
 
@@ -156,6 +158,11 @@ WAT_API int wat_profile_read(wat_handle* h, double* ms, int64_t* launches);
 /* unit-test hooks for single kernels (device pointers; fp32 in/out, converted internally when tc != 0) */
 WAT_API int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float* R, float* C, int32_t M, int32_t N,
                  int32_t K, int32_t act, int32_t tc, void* stream);
+/* the bf16-output epilogues as the encoder launches them (A [M,K], W [N,K], C bf16 device; bias fp32):
+ * seq_T == 0: C [M,N] = act(A W^T + bias) (act 1 = exact GELU, the fc1 kernel); seq_T > 0: fused-QKV split, N = 3D:
+ * C [M,2D] = q|k and vt [M/seq_T, n_head, 64, seq_Tpad] = V transposed per head (keys >= seq_T untouched) */
+WAT_API int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, void* vt, int32_t M, int32_t N, int32_t K,
+                      int32_t act, int32_t seq_T, int32_t seq_Tpad, int32_t n_head, void* stream);
 /* x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D]: fused-QKV GEMM + encoder self-attention (hd 64) */
 WAT_API int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
                       int32_t n_head, int32_t tc, void* stream);

@@ -189,6 +189,51 @@ def encoder_pooled(mel: torch.Tensor, sd: Dict[str, torch.Tensor], n_head: int, 
     return out
 
 
+# --------------------------------------------------------------------------- ASR hand-off consumer
+def _mha(xq, xkv, sd, p, n_head, mask=None):
+    """MultiHeadAttention.forward + qkv_attention (model.py:70-107): self- or cross-attention."""
+    g = lambda k: sd[f"{p}.{k}"].to(xq.dtype)
+    N, Tq, D = xq.shape
+    q = xq @ g("query.weight").T + g("query.bias")
+    k = xkv @ g("key.weight").T
+    v = xkv @ g("value.weight").T + g("value.bias")
+    hd = D // n_head
+    scale = hd ** -0.25
+    q = q.view(N, Tq, n_head, hd).permute(0, 2, 1, 3) * scale
+    k = k.view(N, -1, n_head, hd).permute(0, 2, 3, 1) * scale
+    v = v.view(N, -1, n_head, hd).permute(0, 2, 1, 3)
+    qk = q @ k
+    if mask is not None:
+        qk = qk + mask[:Tq, :Tq]
+    w = torch.softmax(qk.float(), dim=-1).to(xq.dtype)
+    return (w @ v).permute(0, 2, 1, 3).reshape(N, Tq, D) @ g("out.weight").T + g("out.bias")
+
+
+def text_decoder_logits(tokens: torch.Tensor, xa: torch.Tensor, sd: Dict[str, torch.Tensor], n_head: int,
+                        dtype=torch.float32) -> torch.Tensor:
+    """TextDecoder.forward without a kv cache (model.py:200-222): tokens [B, n] int64, xa [B, 1500, d] = ln_post(x) of
+    the audio encoder -> logits [B, n, n_vocab].  The consumer of wat_encoder's x_out in the hand-off test; the decoder
+    itself stays PyTorch."""
+    g = lambda k: sd[f"decoder.{k}"].to(dtype)
+    n = tokens.shape[-1]
+    x = g("token_embedding.weight")[tokens] + g("positional_embedding")[:n]
+    xa = xa.to(dtype)
+    mask = torch.full((n, n), float("-inf")).triu_(1).to(x.device)
+    i = 0
+    while f"decoder.blocks.{i}.attn.query.weight" in sd:
+        p = f"decoder.blocks.{i}"
+        h = _ln(x, g(f"blocks.{i}.attn_ln.weight"), g(f"blocks.{i}.attn_ln.bias"))
+        x = x + _mha(h, h, sd, p + ".attn", n_head, mask)
+        h = _ln(x, g(f"blocks.{i}.cross_attn_ln.weight"), g(f"blocks.{i}.cross_attn_ln.bias"))
+        x = x + _mha(h, xa, sd, p + ".cross_attn", n_head)
+        h = _ln(x, g(f"blocks.{i}.mlp_ln.weight"), g(f"blocks.{i}.mlp_ln.bias"))
+        h = _gelu(h @ g(f"blocks.{i}.mlp.0.weight").T + g(f"blocks.{i}.mlp.0.bias"))
+        x = x + (h @ g(f"blocks.{i}.mlp.2.weight").T + g(f"blocks.{i}.mlp.2.bias"))
+        i += 1
+    x = _ln(x, g("ln.weight"), g("ln.bias"))
+    return (x @ g("token_embedding.weight").T).float()
+
+
 # --------------------------------------------------------------------------- TL-TR head
 def decision_window(time_resolution: float) -> int:
     """model.py:355."""

@@ -1,8 +1,10 @@
 """GPU parity: the CUDA path (through libwat's C ABI) against the CPU oracle on seeded inputs and against
 the fixtures the real reference produced (tests/golden).  Tolerances are BASELINE.json's:
 log-mel 1e-4 relative (|a-b| <= 1e-4*max(1,|ref|)), fp32-mode logits 1e-3 max-abs, bf16-mode logits 3e-2
-max-abs with identical top-5 labels per window (tie-aware: a swap only counts when the reference's own gap
-between the swapped logits exceeds 2x the measured error)."""
+max-abs with identical top-5 labels per window.  The top-5 check is tie-aware with a CONSTANT margin: a swap only
+counts when the reference's own gap between the swapped logit and its 5th-largest logit exceeds TIE_MARGIN =
+2 x 7.8e-3, twice the bf16 noise the reference itself shows when run in bf16 - the margin does not
+move with the error being measured.  Every use reports how many windows needed the margin."""
 import ctypes as C
 import math
 import os
@@ -20,6 +22,9 @@ pytestmark = pytest.mark.gpu
 
 MEL_COLS = np.r_[0:40, 1480:1520, 2960:3000, 40:2960:73]
 TOL_MEL, TOL_FP32, TOL_BF16 = 1e-4, 1e-3, 3e-2
+# bf16-mode intermediates, relative to the tensor's own max |value| (they are not in BASELINE.json's tolerance list, so the
+# bound is ours): pooled per-layer states (fp32 residual stream, 20-row means) and ln_post(x) (row-normalised)
+TOL_POOLED_BF16, TOL_XOUT_BF16 = 1e-2, 2e-2
 
 
 def rel_err(a, ref):
@@ -32,19 +37,35 @@ def max_abs(a, ref):
     return float((torch.as_tensor(a).cpu().double() - torch.as_tensor(ref).cpu().double()).abs().max())
 
 
-def top5_consistent(ours, ref, err):
-    """identical top-5 label sets per window, ignoring swaps across a reference gap smaller than 2*err"""
+TIE_MARGIN = 2 * 7.8e-3          # 2 x the reference's own bf16-vs-fp32 logit noise; a constant
+TIE_STATS = {"windows": 0, "needed_margin": 0}
+
+
+def top5_consistent(ours, ref, err=None):
+    """identical top-5 label sets per window; a label may only differ when the reference's own logit for it lies within
+    TIE_MARGIN of the reference's 5th-largest logit (a genuine near-tie).  `err` is unused (kept for the call sites):
+    the margin does not depend on the measured error."""
     nc = torch.as_tensor(ref).shape[-1]
     ours, ref = torch.as_tensor(ours).cpu().reshape(-1, nc), torch.as_tensor(ref).cpu().reshape(-1, nc)
+    ok = True
     for o, r in zip(ours, ref):
+        TIE_STATS["windows"] += 1
         so, sr = set(torch.topk(o, 5).indices.tolist()), set(torch.topk(r, 5).indices.tolist())
         if so == sr:
             continue
+        TIE_STATS["needed_margin"] += 1
         kth = torch.topk(r, 5).values[-1]
         for idx in so ^ sr:
-            if abs(float(r[idx] - kth)) > 2 * max(err, 1e-6):
-                return False
-    return True
+            if abs(float(r[idx] - kth)) > TIE_MARGIN:
+                ok = False
+    return ok
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _report_tie_stats():
+    yield
+    print(f"\n[top-5] windows checked: {TIE_STATS['windows']}, windows that needed the {TIE_MARGIN:.2e} tie margin: "
+          f"{TIE_STATS['needed_margin']}")
 
 
 _models = {}
@@ -154,6 +175,44 @@ def test_gemm_kernels_vs_torch(tc, M, N, K, act, res):
     assert max_abs(out, ref) <= (2e-4 if tc else 1e-4) * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("M,N,K,kind", [(24000, 5120, 1280, "gelu"), (24000, 1280, 5120, "plain"), (24000, 3840, 1280, "qkv"),
+                                        (1500, 1536, 512, "qkv"), (3001, 2048, 512, "gelu")])
+def test_bf16_epilogues_at_encoder_shapes(M, N, K, kind):
+    """the bf16-output epilogues as the encoder launches them: bias + exact GELU in the 16-epilogue-warp CTA-pair kernel
+    (fc1), plain bf16 (K = 5120), and the fused-QKV split (q|k row-major + V transposed per head), at large-v2 shapes."""
+    g = torch.Generator(device="cpu").manual_seed(N + K)
+    A = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    ref = A.float() @ W.float().T + bias                        # fp32 accumulate of the same bf16 operands (cuBLAS), checked on a sample in fp64
+    rows = torch.randint(0, M, (64,), generator=g).cuda()
+    ref64 = A[rows].double() @ W.double().T + bias.double()
+    assert max_abs(ref[rows], ref64) <= 1e-3
+    if kind == "qkv":
+        T = 1500
+        Bc, H, D = M // T if M % T == 0 else None, N // 192, N // 3
+        if Bc is None:
+            pytest.skip("QKV rows must be whole sequences")
+        Tpad = 1536
+        qk = torch.empty(M, 2 * D, device="cuda", dtype=torch.bfloat16)
+        vt = torch.zeros(Bc, H, 64, Tpad, device="cuda", dtype=torch.bfloat16)
+        _lib.check(L.wat_dbg_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), qk.data_ptr(), vt.data_ptr(), M, N, K, 0, T, Tpad, H, st))
+        torch.cuda.synchronize()
+        assert max_abs(qk.float(), ref[:, :2 * D]) <= 2 ** -7 * max(1.0, float(ref.abs().max()))       # one bf16 rounding of the output
+        v_ref = ref[:, 2 * D:].reshape(Bc, T, H, 64).permute(0, 2, 3, 1)
+        assert max_abs(vt[..., :T].float(), v_ref) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+        assert float(vt[..., T:].abs().max()) == 0.0            # padding keys stay zero
+    else:
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        _lib.check(L.wat_dbg_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), None, M, N, K, int(kind == "gelu"), 0, 0, 0, st))
+        torch.cuda.synchronize()
+        if kind == "gelu":
+            ref = 0.5 * ref * (1 + torch.erf(ref / math.sqrt(2)))
+        assert max_abs(out.float(), ref) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("B,T,H", [(1, 128, 2), (2, 1500, 6), (3, 200, 4)])
 @pytest.mark.parametrize("tc", [0, 1], ids=["simt", "tcgen05"])
 def test_attention_kernels_vs_torch(tc, B, T, H):
@@ -210,6 +269,63 @@ def test_encoder_x_output_and_wrong_shape():
         m.encoder(torch.zeros(1, 80, 2000).cuda())
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
+def test_asr_handoff_x_out_feeds_the_text_decoder(golden_dir, precision, tol):
+    """ONE encoder pass serves tagging and ASR.  wat_encoder's x_out = ln_post(x) goes, as it is, into the
+    reference's TextDecoder (restated in oracle/, weights seeded as in oracle/make_golden.py:decoder_case) and the logits
+    of the first decoding step match what the reference's decoder produced from the reference's own encoder output."""
+    z = golden(golden_dir, "decoder_tiny")
+    d, h, L = synth.MODEL_SHAPES["tiny"]
+    m, sd, _ = model_for("tiny", seed=1, init="lively", precision=precision)
+    dsd = {k: v.cuda() for k, v in synth.synth_decoder_state_dict(d, 2, 1024, 64, seed=1).items()}
+    tokens = torch.from_numpy(z["tokens"]).cuda()
+    for ci in (1, 2):
+        mel = whisper_at.log_mel_spectrogram(synth.synth_clip(ci).cuda(), padding=480000)[:, :3000]
+        x, all_x = m.encoder(mel[None])
+        assert x.dtype == torch.float32 and x.shape == (1, 1500, d)
+        ref_xa = torch.from_numpy(z[f"xa_c{ci}"])
+        assert max_abs(x[0, ::25, ::7], ref_xa) <= (2e-3 if precision == "fp32" else TOL_XOUT_BF16) * max(1.0, float(ref_xa.abs().max()))
+        lg = O.text_decoder_logits(tokens, x.expand(2, -1, -1), dsd, h).cpu()
+        ref = torch.from_numpy(z[f"logits_c{ci}"])
+        assert lg.shape == ref.shape
+        assert max_abs(lg, ref) <= tol * max(1.0, float(ref.abs().max())), (ci, max_abs(lg, ref))
+        assert torch.equal(lg[:, -1].argmax(-1), ref[:, -1].argmax(-1))          # same next token
+        # and the same pass gave the tagging states
+        ref_p = torch.from_numpy(golden(golden_dir, "tiny_lively")[f"pooled_c{ci}"]) if ci == 1 else None
+        if ref_p is not None:
+            assert max_abs(all_x[:, ::5, ::3], ref_p) <= (1e-3 if precision == "fp32" else TOL_POOLED_BF16) * max(1.0, float(ref_p.abs().max()))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """a handle per device in ONE process (not torchrun): the shared-memory opt-ins are per device, every entry point
+    runs on its handle's device and leaves the caller's current device alone"""
+    d, hh, L = synth.MODEL_SHAPES["tiny"]
+    dims = whisper_at.ModelDimensions(80, 1500, d, hh, L, 51865, 448, d, hh, L)
+    sd = synth.synth_state_dict(80, d, L, False, seed=1, init="lively")
+    a = synth.synth_batch(3, start=1)
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):                            # the non-default device first
+        m = whisper_at.Whisper(dims, precision="bf16", max_batch=4)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(dev)
+        torch.cuda.set_device(0)
+        outs.append(m.tag_batch(a.to(dev), at_time_res=10).cpu())
+        assert torch.cuda.current_device() == 0
+        outs.append(m.tag_batch_host(a.pin_memory(), at_time_res=10))
+        mel = whisper_at.log_mel_spectrogram(a[0].to(dev), padding=480000)
+        assert str(mel.device) == dev
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    from whisper_at.tltr import TLTR
+    with torch.cuda.device(1):
+        t = TLTR(527, 4, 384, "mean_mlp", precision="fp32")
+        t.load_state_dict(synth.synth_tltr_state_dict("mean_mlp", 4, 384))
+    x = synth.synth_audio_rep(2, 4, 25, 384)
+    y1 = t(x.to("cuda:0"))                                       # input on another device than the handle's
+    assert str(y1.device) == "cuda:0" and torch.cuda.current_device() == 0
+    t.close()
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
 def test_tiny_low_and_base_batch_vs_reference_fixtures(golden_dir, precision, tol):
     z = golden(golden_dir, "tiny_low_lively")
@@ -256,12 +372,54 @@ def test_baseline_configs_bf16_vs_reference_fixtures(golden_dir, tag, name, n_me
     batch = torch.stack([synth.synth_clip(1), synth.synth_clip(2), synth.synth_clip(1)]).cuda()
     for res in ress:
         lg = m.tag_batch(batch, at_time_res=res)
-        ref = z[f"logits_c1_r{res}_a0"]
-        err = max_abs(lg[0], ref)
-        assert err <= TOL_BF16, (tag, res, err)
-        assert top5_consistent(lg[0], ref, err)
+        for pos, ci in ((0, 1), (1, 2)):                       # two different clips against the reference's logits
+            ref = z[f"logits_c{ci}_r{res}_a0"]
+            err = max_abs(lg[pos], ref)
+            assert err <= TOL_BF16, (tag, ci, res, err)
+            assert top5_consistent(lg[pos], ref)
         assert torch.equal(lg[0], lg[2])                       # same clip at two batch positions: bit-identical
         assert not torch.equal(lg[0], lg[1])
+    # bf16 intermediates against the reference's fp32 ones: every layer's pooled state and ln_post(x) (the ASR hand-off)
+    mel = torch.stack([whisper_at.log_mel_spectrogram(synth.synth_clip(ci).cuda(), n_mels=n_mels, padding=480000)[:, :3000]
+                       for ci in (1, 2)])
+    x, all_x = m.encoder(mel)
+    for pos, ci in ((0, 1), (1, 2)):
+        ref_p, ref_x = torch.from_numpy(z[f"pooled_c{ci}"]), torch.from_numpy(z[f"xout_c{ci}"])
+        ep = max_abs(all_x[pos][:, ::5, ::3], ref_p) / max(1.0, float(ref_p.abs().max()))
+        ex = max_abs(x[pos][::25, ::7], ref_x) / max(1.0, float(ref_x.abs().max()))
+        assert ep <= TOL_POOLED_BF16, (tag, ci, "pooled", ep)
+        assert ex <= TOL_XOUT_BF16, (tag, ci, "ln_post(x)", ex)
+    _models.clear()
+    torch.cuda.empty_cache()
+
+
+def test_benchmarked_shape_large_v2_128_clips(golden_dir):
+    """The configuration bench.py times: large-v2 / 128-bin mel / full TL-TR / 128 clips in one call.  The fixture clips
+    sit at batch positions 0, 63 and 127 (and clip 2 at 1 and 126) among rolled filler clips; every copy must match the
+    reference's logits and be bit-identical to the other copies, through the device entry point (wat_tag) and the host
+    entry point (wat_tag_host, 8 H2D pieces overlapped with the mel kernel)."""
+    z = golden(golden_dir, "large_v2_m128_lively")
+    m, sd, h = model_for("large-v2", n_mels=128, low=False, seed=1, init="lively", precision="bf16", max_batch=128)
+    c1, c2 = synth.synth_clip(1), synth.synth_clip(2)
+    filler = synth.synth_batch(6, start=3)
+    clips = [torch.roll(filler[i % 6], 1600 * (i // 6)) for i in range(128)]
+    for pos, c in ((0, c1), (63, c1), (127, c1), (1, c2), (126, c2)):
+        clips[pos] = c
+    host = torch.stack(clips).pin_memory()
+    dev = m.tag_batch(host.cuda(), at_time_res=10)
+    via_host = m.tag_batch_host(host, at_time_res=10)
+    assert torch.equal(dev.cpu(), via_host)
+    for pos, ci in ((0, 1), (63, 1), (127, 1), (1, 2), (126, 2)):
+        ref = z[f"logits_c{ci}_r10_a0"]
+        err = max_abs(dev[pos], ref)
+        assert err <= TOL_BF16, (pos, ci, err)
+        assert top5_consistent(dev[pos], ref)
+    assert torch.equal(dev[0], dev[63]) and torch.equal(dev[0], dev[127]) and torch.equal(dev[1], dev[126])
+    assert not torch.equal(dev[0], dev[1])
+    lg2 = m.tag_batch(host[[0, 1]].cuda(), at_time_res=2)       # second resolution of the large fixture (S = 15)
+    for pos, ci in ((0, 1), (1, 2)):
+        ref = z[f"logits_c{ci}_r2_a0"]
+        assert max_abs(lg2[pos], ref) <= TOL_BF16 and top5_consistent(lg2[pos], ref)
     _models.clear()
     torch.cuda.empty_cache()
 
@@ -375,6 +533,9 @@ def test_pooled_feature_export_vs_oracle(tmp_path):
     assert feat.shape == (4, 25, 384) and feat.dtype == np.float32
     ref = O.encoder_pooled(O.log_mel_clip(clip)[None], sd, h)[0][:, :25]
     assert max_abs(feat, ref) <= 1e-3 * max(1.0, float(ref.abs().max()))
+    m16, _, _ = model_for("tiny", seed=1, init="lively", precision="bf16")      # the default engine of load_model()
+    feat16 = features.pooled_features(m16, clip, seconds=10.0)
+    assert max_abs(feat16, ref) <= TOL_POOLED_BF16 * max(1.0, float(ref.abs().max()))
     features.save_feature_npz(str(tmp_path / "c.npz"), feat)
     assert np.array_equal(features.load_feature_npz(str(tmp_path / "c.npz")), feat)
 

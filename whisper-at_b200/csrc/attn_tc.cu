@@ -346,13 +346,9 @@ static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuin
 
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int Tpad,
                            int n_head, cudaStream_t st, long long* trace) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0, attr_mask_tr = 0;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
   const int D = n_head * 64;
   if (Tpad % AT_KV || Tpad < ((T + AT_KV - 1) / AT_KV) * AT_KV) return cudaErrorInvalidValue;
   CUtensorMap tmQ, tmK, tmVT;

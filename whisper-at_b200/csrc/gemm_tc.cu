@@ -516,12 +516,8 @@ static bool make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
 template <int BN>
 static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (cudaError_t e = opt_in_smem(gemm_tc_kernel<BN>, Cfg::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
   CUtensorMap tmA, tmB;
   if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, BN)) return cudaErrorInvalidValue;
@@ -541,12 +537,8 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
 template <int EW>
 static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   using Cfg2 = Tc2Cfg<EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW>, Cfg2::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
   CUtensorMap tmA, tmB;
   if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, 128)) return cudaErrorInvalidValue;      // each CTA loads half of the 256 W rows

@@ -8,6 +8,20 @@
 
 namespace wat {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process that drives several GPUs (two handles
+// on two devices) must opt in on each of them.  `done_mask` is the launcher's own bit set of configured devices.
+template <typename K>
+inline cudaError_t opt_in_smem(K kernel, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_mask |= bit;
+  return e;
+}
+
 // ---------------------------------------------------------------------------------- mel.cu
 struct MelTables {
   int n_mels = 0;

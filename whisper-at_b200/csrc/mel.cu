@@ -268,13 +268,9 @@ size_t mel_power_smem_bytes() {
 cudaError_t launch_mel_power(const MelTables& tb, const void* pcm, bool pcm_i16, long long clip_stride, const int* n_valid_arr,
                              int n_valid_all, int n_pad, int B, int n_frames, int n_store, int frames_alloc,
                              float* logspec, float* clip_max, cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   const size_t smem = mel_power_smem_bytes();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = opt_in_smem(mel_power_kernel, (int)smem, attr_mask); e != cudaSuccess) return e;
   fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(clip_max, -INFINITY, B);
   dim3 grid((n_frames + MEL_F - 1) / MEL_F, B);
   mel_power_kernel<<<grid, MEL_THREADS, smem, st>>>(pcm, pcm_i16 ? 1 : 0, clip_stride, n_valid_arr, n_valid_all, n_pad, n_frames, n_store,

@@ -249,13 +249,9 @@ cudaError_t launch_layernorm_pool20(const float* x, const float* gamma, const fl
   const int P = T / 20;
   const int grid = B * P, block = 320;
   const size_t smem = (size_t)10 * D * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(layernorm_pool20_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 1280 * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(layernorm_pool20_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 1280 * 4);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask_h = 0, attr_mask_f = 0;
+  if (cudaError_t e = opt_in_smem(layernorm_pool20_kernel<__nv_bfloat16>, 10 * 1280 * 4, attr_mask_h); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(layernorm_pool20_kernel<float>, 10 * 1280 * 4, attr_mask_f); e != cudaSuccess) return e;
   if (out_bf16) layernorm_pool20_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(x, gamma, beta, D, (__nv_bfloat16*)out, pooled, layer, L, P);
   else layernorm_pool20_kernel<float><<<grid, block, smem, st>>>(x, gamma, beta, D, (float*)out, pooled, layer, L, P);
   return cudaGetLastError();
@@ -524,8 +520,9 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
   const size_t smem = sizeof(float) * T * (T + 1);
   const float scale2 = 1.0f / sqrtf((float)hd);           // (hd^-0.25)^2
   if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(attn_small_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-    cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    static unsigned long long attr_mask_f = 0, attr_mask_h = 0;
+    if (cudaError_t e = opt_in_smem(attn_small_kernel<float, float>, 80 * 1024, attr_mask_f); e != cudaSuccess) return e;
+    if (cudaError_t e = opt_in_smem(attn_small_kernel<__nv_bfloat16, __nv_bfloat16>, 80 * 1024, attr_mask_h); e != cudaSuccess) return e;
   }
   if (in_bf16 && out_bf16 && T <= 32 && (hd & 15) == 0) {
     attn_small_mma_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2);

@@ -51,6 +51,21 @@ const char* const kProfNames[PC_COUNT] = {"mel", "layout", "gemm", "attention", 
 
 struct ProfRec { int cls; cudaEvent_t a, b; };
 
+// Every entry point runs on the handle's device and puts the caller's current device back on exit (a ctypes caller that
+// drives several GPUs from one thread must not have its device switched under it).
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h)                                                                                  \
+  DeviceGuard guard__((h)->device);                                                                   \
+  if (guard__.err != cudaSuccess) return fail(WAT_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(guard__.err))
+
 struct Slot {            // where a state_dict tensor lands on the device
   float* dst = nullptr;
   int64_t numel = 0;
@@ -320,7 +335,9 @@ int ensure_ws(wat_handle* h, int B) {
   if ((rc = grow(h, h->xn, es * rows_cap * d))) return rc;
   if ((rc = grow(h, h->qkv, es * rows_cap * 3 * d))) return rc;
   if ((rc = grow(h, h->att, es * rows_cap * d))) return rc;
-  if ((rc = grow(h, h->hbuf, es * rows_cap * 4 * d))) return rc;
+  // hbuf also holds the conv1 im2col rows [Bc*3000, 3*n_mels], which exceed rows*4d when d < 1.5 n_mels
+  const int64_t hbuf_elems = std::max(rows_cap * 4 * d, h->head_only ? (int64_t)0 : (int64_t)Bc * 3000 * 3 * h->cfg.n_mels);
+  if ((rc = grow(h, h->hbuf, es * hbuf_elems))) return rc;
   if (h->bf16 && !h->head_only) {
     if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;   // zeroed: the 36 padding keys stay 0
   }
@@ -468,7 +485,6 @@ int check_ready(wat_handle* h, bool needs_encoder = true) {
   if (!h) return fail(WAT_ERR_INVALID, "null handle");
   if (!h->finalized) return fail(WAT_ERR_STATE, "wat_finalize has not been called");
   if (needs_encoder && h->head_only) return fail(WAT_ERR_STATE, "head-only handle (wat_head_create): no mel / encoder on it");
-  CU(cudaSetDevice(h->device));
   return 0;
 }
 
@@ -508,6 +524,9 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
   if (cfg->n_audio_state <= 0 || cfg->n_audio_state % 128 || cfg->n_audio_head * 64 != cfg->n_audio_state)
     return fail(WAT_ERR_INVALID, "n_audio_state must be a multiple of 128 with head_dim 64 (got d=%d, heads=%d)",
                 cfg->n_audio_state, cfg->n_audio_head);
+  if (cfg->n_audio_state > 1280)
+    return fail(WAT_ERR_INVALID, "n_audio_state %d not supported: the LayerNorm / pooling kernels hold a row in registers (d <= 1280, Whisper large)",
+                cfg->n_audio_state);
   if (cfg->n_audio_layer < 1 || cfg->n_audio_layer > 128) return fail(WAT_ERR_INVALID, "bad n_audio_layer");
   if (cfg->precision != WAT_FP32 && cfg->precision != WAT_BF16) return fail(WAT_ERR_INVALID, "bad precision");
   if (cfg->n_class < 1) return fail(WAT_ERR_INVALID, "bad n_class");
@@ -569,7 +588,7 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
 int wat_set_weight(wat_handle* h, const char* key, const float* host_data, int64_t numel) {
   if (!h || !key || !host_data) return fail(WAT_ERR_INVALID, "null argument");
   if (h->finalized) return fail(WAT_ERR_STATE, "handle already finalized");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   if (!strncmp(key, "decoder.", 8)) return WAT_OK;                // ASR decoder: not on this path
   std::string norm(key);
   if (h->head_only) {                                             // TLTR's own keys: [module.]time_tr.* -> at_model.time_tr.*
@@ -598,7 +617,7 @@ int wat_set_weight(wat_handle* h, const char* key, const float* host_data, int64
 int wat_finalize(wat_handle* h) {
   if (!h) return fail(WAT_ERR_INVALID, "null handle");
   if (h->finalized) return WAT_OK;
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   for (auto& kv : h->slots)
     if (!kv.second.set && !kv.second.optional) return fail(WAT_ERR_STATE, "Missing key in state_dict: %s", kv.first.c_str());
   if (h->bf16) {
@@ -620,7 +639,7 @@ int wat_finalize(wat_handle* h) {
 
 int wat_destroy(wat_handle* h) {
   if (!h) return WAT_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->owned) cudaFree(p);
   Buf* bufs[] = {&h->x, &h->x2, &h->xn, &h->qkv, &h->vt, &h->att, &h->hbuf, &h->logspec, &h->clipmax, &h->melT,
@@ -638,7 +657,7 @@ int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32
                int32_t n_pad, int32_t B, int32_t n_frames, int32_t clamp_scope, float* mel_out, void* stream) {
   if (!h) return fail(WAT_ERR_INVALID, "null handle");
   if (h->head_only) return fail(WAT_ERR_STATE, "head-only handle (wat_head_create): no mel tables on it");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   int rc = 0;
   if (!pcm || !mel_out || B < 1 || n_samples < 1 || n_pad < 0 || n_frames < 1) return fail(WAT_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -656,6 +675,7 @@ int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32
 int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* pooled_out, float* x_out, void* stream) {
   int rc = check_ready(h);
   if (rc) return rc;
+  ON_DEVICE(h);
   if (!mel || !pooled_out || B < 1) return fail(WAT_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   h->cur_stream = st;
@@ -674,6 +694,7 @@ int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int
              float* logits_out, void* stream) {
   int rc = check_ready(h, false);
   if (rc) return rc;
+  ON_DEVICE(h);
   if (!pooled || !logits_out || B < 1) return fail(WAT_ERR_INVALID, "bad argument");
   if ((rc = ensure_ws(h, std::min(B, h->cfg.max_batch)))) return rc;
   h->cur_stream = (cudaStream_t)stream;
@@ -731,6 +752,7 @@ static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_strid
                     int piece_clips = 0) {
   int rc = check_ready(h);
   if (rc) return rc;
+  ON_DEVICE(h);
   if (!pcm || !logits_out || B < 1 || n_samples < 1 || n_samples > 480000) return fail(WAT_ERR_INVALID, "bad argument (clips are <= 480000 samples)");
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
   h->cur_stream = st;
@@ -765,9 +787,13 @@ static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t 
                          int32_t n_samples, int32_t B, int32_t dw, float* logits_host) {
   int rc = check_ready(h);
   if (rc) return rc;
+  ON_DEVICE(h);
   if (!pcm_host || !logits_host || B < 1 || n_samples < 1 || n_samples > 480000 || clip_stride < n_samples)
     return fail(WAT_ERR_INVALID, "bad argument");
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
+  if (n_valid)
+    for (int i = 0; i < B; ++i)
+      if (n_valid[i] < 0 || n_valid[i] > n_samples) return fail(WAT_ERR_INVALID, "n_valid[%d] out of range", i);
   const int S = (75 + dw - 1) / dw;
   cudaStream_t st = h->own_stream;
   const size_t pcm_bytes = (i16 ? sizeof(int16_t) : sizeof(float)) * ((size_t)(B - 1) * clip_stride + n_samples);
@@ -785,7 +811,13 @@ static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t 
     CU(cudaMemcpyAsync((char*)h->pcm_stage.p + off, (const char*)pcm_host + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
     CU(cudaEventRecord(h->piece_ev[p], h->copy_stream));
   }
-  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st, h->piece_ev, piece_clips))) return rc;
+  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st, h->piece_ev, piece_clips))) {
+    // the H2D pieces (and whatever was launched before the failure) may still be in flight: the caller is free to release
+    // pcm_host as soon as we return, and the next call reuses pcm_stage
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(st);
+    return rc;
+  }
   CU(cudaMemcpyAsync(logits_host, h->logits.p, sizeof(float) * (size_t)B * S * h->cfg.n_class, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return WAT_OK;
@@ -824,7 +856,7 @@ const char* wat_profile_class_name(int32_t i) { return (i >= 0 && i < PC_COUNT) 
 
 int wat_profile_read(wat_handle* h, double* ms, int64_t* launches) {
   if (!h || !ms || !launches) return fail(WAT_ERR_INVALID, "null argument");
-  CU(cudaSetDevice(h->device));
+  ON_DEVICE(h);
   for (int i = 0; i < PC_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
   for (size_t i = 0; i < h->prof_used; ++i) {
     CU(cudaEventSynchronize(h->prof[i].b));
@@ -887,6 +919,30 @@ int wat_dbg_gemm(const float* A, const float* W, const float* bias, const float*
   if (Cb) cudaFree(Cb);
   if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "launch_gemm_tc: %s", cudaGetErrorString(e));
   if (e2 != cudaSuccess) return fail(WAT_ERR_CUDA, "gemm_tc execution: %s", cudaGetErrorString(e2));
+  return WAT_OK;
+}
+
+// The bf16-output epilogues of the tcgen05 GEMM exactly as the encoder launches them: A [M, K], W [N, K] bf16 device, bias fp32.
+//   seq_T == 0 : C [M, N] bf16 = act(A W^T + bias)           (fc1: act = 1 selects the 16-epilogue-warp GELU kernel)
+//   seq_T  > 0 : fused-QKV split epilogue, N = 3D: C [M, 2D] bf16 = (q | k), vt [M / seq_T, n_head, 64, seq_Tpad] = V^T
+int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, void* vt, int32_t M, int32_t N, int32_t K,
+                      int32_t act, int32_t seq_T, int32_t seq_Tpad, int32_t n_head, void* stream) {
+  if (!A || !W || !C || M < 1 || N < 1 || K < 1) return fail(WAT_ERR_INVALID, "bad argument");
+  if (seq_T > 0 && (!vt || M % seq_T || n_head * 64 * 3 != N || seq_Tpad < seq_T)) return fail(WAT_ERR_INVALID, "bad QKV shape");
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GemmTc g;
+  memset(&g, 0, sizeof(g));
+  g.A = (const __nv_bfloat16*)A; g.lda = K; g.W = (const __nv_bfloat16*)W; g.bias = bias; g.C = C;
+  g.M = M; g.N = N; g.K = K; g.act = act;
+  if (seq_T > 0) {
+    g.epi = TC_EPI_QKV; g.ldc = 2 * (N / 3); g.vt = (__nv_bfloat16*)vt; g.seq_T = seq_T; g.seq_Tpad = seq_Tpad; g.n_head = n_head;
+  } else {
+    g.epi = TC_EPI_BF16; g.ldc = N;
+  }
+  cudaError_t e = launch_gemm_tc(g, sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "launch_gemm_tc: %s", cudaGetErrorString(e));
   return WAT_OK;
 }
 

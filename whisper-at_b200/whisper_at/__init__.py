@@ -5,9 +5,12 @@ pad_or_trim, load_audio, parse_at_label, print_label_name, print_support_languag
 transcribe.  Compute is done by libwat.so (hand-written sm_100a CUDA, see ../csrc and include/wat.h)."""
 from __future__ import annotations
 
+import hashlib
 import io
 import os
+import urllib.parse
 import urllib.request
+import warnings
 from typing import List, Optional, Union
 
 import torch
@@ -39,12 +42,18 @@ def available_models() -> List[str]:
 
 
 def _fetch(url: str, root: str, in_memory: bool) -> Union[bytes, str]:
-    """Cached download with the reference's cache-file naming (__init__.py:68-112): basename of the URL."""
+    """Cached download with the reference's cache-file naming (__init__.py:68-112): basename of the URL *path*
+    ("tiny_ori.pth" for ".../tiny_ori.pth?dl=1"), so caches written by the reference are reused.  The OpenAI URLs carry
+    the file's sha256 as their second-to-last path component; it is checked (the reference has the check commented out)."""
     os.makedirs(root, exist_ok=True)
-    target = os.path.join(root, os.path.basename(url))
+    path = urllib.parse.urlparse(url).path
+    target = os.path.join(root, os.path.basename(path))
+    parts = path.split("/")
+    expected_sha = parts[-2] if len(parts) >= 2 and len(parts[-2]) == 64 and all(c in "0123456789abcdef" for c in parts[-2]) else None
     if os.path.exists(target) and not os.path.isfile(target):
         raise RuntimeError(f"{target} exists and is not a regular file")
-    if not os.path.isfile(target):
+    fresh = not os.path.isfile(target)
+    if fresh:
         try:
             with urllib.request.urlopen(url) as src, open(target + ".part", "wb") as dst:
                 while True:
@@ -55,6 +64,17 @@ def _fetch(url: str, root: str, in_memory: bool) -> Union[bytes, str]:
             os.replace(target + ".part", target)
         except Exception as e:
             raise RuntimeError(f"could not download {url} to {target} ({e}); place the file there manually") from e
+    if expected_sha is not None:
+        hsh = hashlib.sha256()
+        with open(target, "rb") as f:
+            for buf in iter(lambda: f.read(1 << 20), b""):
+                hsh.update(buf)
+        if hsh.hexdigest() != expected_sha:
+            if fresh:
+                os.remove(target)
+                raise RuntimeError(f"{url} has been downloaded but its SHA256 checksum does not match; retry loading the model")
+            # a file that was already in the cache is used as it is, like the reference does (its check is commented out)
+            warnings.warn(f"{target} exists, but its SHA256 checksum does not match the one in {url}")
     if in_memory:
         with open(target, "rb") as f:
             return f.read()
@@ -63,7 +83,7 @@ def _fetch(url: str, root: str, in_memory: bool) -> Union[bytes, str]:
 
 def _torch_load(src, device):
     with (io.BytesIO(src) if isinstance(src, bytes) else open(src, "rb")) as fp:
-        return torch.load(fp, map_location=device)
+        return torch.load(fp, map_location=device, weights_only=True)      # checkpoints are plain dicts of tensors / ints
 
 
 def load_model(name: str, device: Optional[Union[str, torch.device]] = None, download_root: str = None,

@@ -63,6 +63,7 @@ _SIGS = {
     "wat_profile_class_name": (C.c_char_p, [_i32]),
     "wat_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "wat_dbg_gemm": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "wat_dbg_gemm_bf16": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_attention": (C.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_tma_overlap_probe": (C.c_int, []),
 }

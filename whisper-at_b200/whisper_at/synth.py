@@ -174,6 +174,39 @@ def synth_state_dict(n_mels: int, d: int, n_layer: int, low: bool, seed: int = 0
     return out
 
 
+def decoder_state_shapes(d: int, n_layer: int, n_vocab: int, n_ctx: int) -> "OrderedDict[str, tuple]":
+    """Parameters of the reference's TextDecoder (model.py:180-198) for the ASR hand-off test."""
+    s = OrderedDict()
+    s["decoder.token_embedding.weight"] = (n_vocab, d)
+    s["decoder.positional_embedding"] = (n_ctx, d)
+    for i in range(n_layer):
+        p = f"decoder.blocks.{i}"
+        s.update(_block_shapes(p, d))
+        for k, shape in _block_shapes(p, d).items():
+            if ".attn." in k or ".attn_ln." in k:
+                s[k.replace(".attn.", ".cross_attn.").replace(".attn_ln.", ".cross_attn_ln.")] = shape
+    s["decoder.ln.weight"] = (d,)
+    s["decoder.ln.bias"] = (d,)
+    return s
+
+
+def synth_decoder_state_dict(d: int, n_layer: int, n_vocab: int = 1024, n_ctx: int = 64, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """Seeded 'lively' weights of a small TextDecoder: the consumer of `ln_post(x)` in the hand-off test."""
+    out: Dict[str, torch.Tensor] = OrderedDict()
+    for name, shape in decoder_state_shapes(d, n_layer, n_vocab, n_ctx).items():
+        g = torch.Generator().manual_seed(_seed_for(name, seed))
+        if "_ln." in name or name.startswith("decoder.ln."):
+            w = 0.5 + torch.rand(shape, generator=g) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("embedding.weight") or name.endswith("positional_embedding"):
+            w = 0.3 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            w = 0.1 * torch.randn(shape, generator=g)
+        else:
+            w = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(shape[1])
+        out[name] = w.to(torch.float32).contiguous()
+    return out
+
+
 def tltr_state_shapes(mode: str, n_layer: int, rep_dim: int, label_dim: int = 527) -> "OrderedDict[str, tuple]":
     """Parameters of the training recipe's TLTR module for a mode string (src/whisper_at_train/models.py:49-106),
     under the module's own key names."""

@@ -51,6 +51,7 @@ class TLTR:
         cfg = _lib.WatHeadConfig(rep_dim, n_layer, inter, label_dim, code, nt, nl,
                                  _lib.WAT_BF16 if precision == "bf16" else _lib.WAT_FP32, max_batch)
         h = C.c_void_p()
+        self._device = torch.device("cuda", torch.cuda.current_device())      # the handle is bound to the device current at creation
         _lib.check(_lib.lib().wat_head_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self._loaded = False
@@ -70,11 +71,12 @@ class TLTR:
         assert audio_rep.ndim == 4 and audio_rep.shape[1] == self.n_layer and audio_rep.shape[3] == self.rep_dim, \
             "audio_rep must be [B, n_layer, T', rep_dim]"
         dev = audio_rep.device
-        x = audio_rep.to(device="cuda", dtype=torch.float32).contiguous()
-        B, _, Tp, _ = x.shape
-        out = torch.empty(B, self.label_dim, device="cuda", dtype=torch.float32)
-        _lib.check(_lib.lib().wat_head_forward(self._h, C.c_void_p(x.data_ptr()), B, Tp, C.c_void_p(out.data_ptr()),
-                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        with torch.cuda.device(self._device):
+            x = audio_rep.to(device=self._device, dtype=torch.float32).contiguous()
+            B, _, Tp, _ = x.shape
+            out = torch.empty(B, self.label_dim, device=self._device, dtype=torch.float32)
+            _lib.check(_lib.lib().wat_head_forward(self._h, C.c_void_p(x.data_ptr()), B, Tp, C.c_void_p(out.data_ptr()),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out.to(dev)
 
     __call__ = forward

@@ -70,9 +70,19 @@ def transcribe(
             all_x = model._encode(segs[c0:c0 + chunk], precision=precision)
             if all_x.ndim == 3:
                 all_x = all_x[None]
+            # windows that share an at_start go through the head as ONE batch (wat_tltr takes [n, L, 75 - at_start, d]);
+            # there are at most window / gcd(window, 3000) distinct values
+            groups = {}
             for i, seek in enumerate(seeks[c0:c0 + chunk]):
-                at_start = math.floor(seek % at_decision_window / 40)                            # transcribe.py:255
-                audio_tag = model._head(all_x[i][:, at_start:, :], at_time_res, precision=precision).cpu()
+                groups.setdefault(math.floor(seek % at_decision_window / 40), []).append((i, seek))      # transcribe.py:255
+            placed = {}
+            for at_start, members in groups.items():
+                idx = torch.tensor([i for i, _ in members], device=all_x.device)
+                tags = model._head(all_x.index_select(0, idx)[:, :, at_start:, :], at_time_res, precision=precision).cpu()
+                for (i, _), audio_tag in zip(members, tags):
+                    placed[i] = audio_tag
+            for i, seek in enumerate(seeks[c0:c0 + chunk]):       # rows are written in window order: a later window overwrites
+                audio_tag = placed[i]
                 cur_start = math.floor(seek / at_decision_window)
                 cur_end = min(all_audio_tags.shape[0], cur_start + audio_tag.shape[0])
                 all_audio_tags[cur_start:cur_end, :] = audio_tag[0:cur_end - cur_start, :]       # transcribe.py:261-263
