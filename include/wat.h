@@ -15,7 +15,9 @@
  * Conventions: plain pointers and sizes only; device pointers are owned by the caller (e.g. torch tensors);
  * `stream` is a cudaStream_t passed as void*; every function returns 0 on success or a negative wat_status,
  * and wat_last_error() returns a thread-local message.  No C++ exception crosses the boundary.  A handle is
- * bound to the CUDA device that was current at wat_create and is not re-entrant (one handle per thread/stream).
+ * bound to the CUDA device that was current at wat_create and is not re-entrant (one handle per host thread).  Calls on
+ * one handle share its workspace: they are ordered on the device in call order even when they are issued on different
+ * streams (an event dependency is inserted), and every entry point restores the caller's current device before returning.
  * There is no CPU fallback: without a CUDA device every compute call returns WAT_ERR_CUDA.
  */
 #ifndef WAT_H_
@@ -163,6 +165,13 @@ WAT_API int wat_dbg_gemm(const float* A, const float* W, const float* bias, cons
  * C [M,2D] = q|k and vt [M/seq_T, n_head, 64, seq_Tpad] = V transposed per head (keys >= seq_T untouched) */
 WAT_API int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, void* vt, int32_t M, int32_t N, int32_t K,
                       int32_t act, int32_t seq_T, int32_t seq_Tpad, int32_t n_head, void* stream);
+/* a LayerNorm folded into the GEMM that consumes it, chained as the bf16 encoder does (see DESIGN.md "LayerNorm folding"):
+ * x = R + A1 W1^T + bias1 (fp32; the epilogue also leaves xb = bf16(x), per-slice row statistics and 20-row pooled means),
+ * then out = act(LN(x; gamma, beta) W2^T + bias2) as rstd (xb W2'^T - mean colsum) + bias2'.  All pointers device. */
+WAT_API int wat_dbg_ln_slices(int32_t M, int32_t D, int32_t K1, int32_t pair);
+WAT_API int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const float* R, float* x, void* xb, float* stats,
+                    float* pooled, const float* W2, const float* gamma, const float* beta, const float* bias2, void* out, int32_t M,
+                    int32_t D, int32_t K1, int32_t N2, int32_t act, int32_t pair, void* stream);
 /* x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D]: fused-QKV GEMM + encoder self-attention (hd 64) */
 WAT_API int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
                       int32_t n_head, int32_t tc, void* stream);

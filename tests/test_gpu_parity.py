@@ -213,6 +213,46 @@ def test_bf16_epilogues_at_encoder_shapes(M, N, K, kind):
         assert max_abs(out.float(), ref) <= 2 ** -7 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("M,D,K1,N2,act,pair", [(3000, 1280, 1280, 5120, 1, 1), (3000, 1280, 5120, 3840, 0, 1), (1500, 384, 384, 1536, 1, -1),
+                                                (1500, 768, 768, 768, 0, -1), (777, 512, 2048, 1024, 0, 1), (100, 512, 512, 512, 1, 0)])
+def test_layernorm_folded_into_gemm(M, D, K1, N2, act, pair):
+    """the bf16 encoder has no LayerNorm kernel: the producing GEMM's epilogue leaves bf16(x), per-slice row statistics and the
+    20x pooled means; the consuming GEMM computes LN(x) W^T + b as rstd (x W'^T - mean colsum) + b'.  Both halves against torch."""
+    g = torch.Generator(device="cpu").manual_seed(M + D + K1)
+    A1 = torch.randn(M, K1, generator=g).cuda().bfloat16()
+    W1 = (torch.randn(D, K1, generator=g) / math.sqrt(K1)).cuda().bfloat16()
+    b1 = torch.randn(D, generator=g).cuda()
+    R = (torch.randn(M, D, generator=g) * 2 + 0.7 * torch.randn(M, 1, generator=g)).cuda()       # rows with their own mean
+    W2 = (torch.randn(N2, D, generator=g) / math.sqrt(D)).cuda()
+    gamma = (0.5 + torch.rand(D, generator=g)).cuda()
+    beta = (0.3 * torch.randn(D, generator=g)).cuda()
+    b2 = torch.randn(N2, generator=g).cuda()
+    L = _lib.lib()
+    np_ = L.wat_dbg_ln_slices(M, D, K1, pair)
+    x = torch.empty(M, D, device="cuda")
+    xb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((M, np_, 2), float("nan"), device="cuda")
+    pooled = torch.full((M // 1500, 1, 75, D), float("nan"), device="cuda") if M % 1500 == 0 else None
+    out = torch.empty(M, N2, device="cuda", dtype=torch.bfloat16)
+    _lib.check(L.wat_dbg_ln_gemm(A1.data_ptr(), W1.data_ptr(), b1.data_ptr(), R.data_ptr(), x.data_ptr(), xb.data_ptr(), stats.data_ptr(),
+                                 pooled.data_ptr() if pooled is not None else None, W2.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 b2.data_ptr(), out.data_ptr(), M, D, K1, N2, act, pair, torch.cuda.current_stream().cuda_stream))
+    x_ref = R.double() + A1.double() @ W1.double().T + b1.double()
+    assert max_abs(x, x_ref) <= 2e-4 * max(1.0, float(x_ref.abs().max()))
+    assert torch.equal(xb, x.bfloat16())                                                 # the copy is the rounded fp32 row
+    assert max_abs(stats[..., 0].sum(1), x.double().sum(1)) <= 1e-3 and max_abs(stats[..., 1].sum(1), (x.double() ** 2).sum(1)) <= 2e-2
+    if pooled is not None:
+        assert max_abs(pooled[:, 0], xb.double().reshape(-1, 75, 20, D).mean(2)) <= 1e-6 * max(1.0, float(x_ref.abs().max()))
+        assert max_abs(pooled[:, 0], x.double().reshape(-1, 75, 20, D).mean(2)) <= 2e-3 * max(1.0, float(x_ref.abs().max()))
+    ln = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    ref = ln @ W2.double().T + b2.double()
+    if act:
+        ref = 0.5 * ref * (1 + torch.erf(ref / math.sqrt(2)))
+    # vs the explicit form with the same operand roundings (bf16 LN output would be the alternative): bf16-level agreement
+    assert max_abs(out.float(), ref) <= 2.5e-2 * max(1.0, float(ref.abs().max())), max_abs(out.float(), ref)
+    assert float((out.float() - ref.float()).abs().mean()) <= 4e-3 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("B,T,H", [(1, 128, 2), (2, 1500, 6), (3, 200, 4)])
 @pytest.mark.parametrize("tc", [0, 1], ids=["simt", "tcgen05"])
 def test_attention_kernels_vs_torch(tc, B, T, H):

@@ -29,9 +29,10 @@ template <int BN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 3 : 5;
   static constexpr int TMEM_COLS = 2 * BN;                       // 512 or 256: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int WARP_STAGE_BYTES = 7168;                  // per epilogue warp: 32 x 36 float transpose tile + 32 x 8 float2 row-statistics slots
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 8 * WARP_STAGE_BYTES + 256 /*barriers*/;
 };
 
 struct GemmTcDev {
@@ -39,7 +40,13 @@ struct GemmTcDev {
   void* C; long long ldc;
   const float* R; long long ldr; int r_mod;
   int M, N, K, act, epi;
+  int tma_store;           // bf16 outputs leave through smem + TMA store (CTA-pair kernel)
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
+  // fp32 epilogues as PRODUCER of the next LayerNorm (see kernels.h GemmTc): bf16 copy, per-slice row statistics
+  __nv_bfloat16* xb; long long ldxb;
+  float* stats; int stats_np;
+  // LayerNorm of the A rows folded into this GEMM (CONSUMER)
+  const float* ln_stats; int ln_np; const float* ln_colsum;
   long long* trace;        // optional clock trace of cluster 0 (test hook)
 };
 
@@ -61,18 +68,108 @@ __device__ __forceinline__ void load_residual_chunk(const GemmTcDev& g, int row_
   }
 }
 
+// ---- LayerNorm folded into the consuming GEMM.  With W' = W diag(gamma) (bf16), cs[n] = sum_k W'[n,k] and
+// b'[n] = b[n] + sum_k W[n,k] beta[k] (prepared once, launch_fold_ln_weights):
+//     LN(x) W^T + b  =  rstd (x W'^T - mean cs) + b'
+// so the GEMM reads the un-normalised bf16 copy of x its producer's epilogue wrote, and the row's (mean, rstd) come from the
+// per-slice (sum, sum of squares) partials the same epilogue left in `stats` (summed here in a fixed order).
+__device__ __forceinline__ void ln_row_scalars(const GemmTcDev& g, int row, bool row_ok, float& mean, float& rstd) {
+  mean = 0.f; rstd = 0.f;
+  if (!row_ok) return;
+  const float2* sp = reinterpret_cast<const float2*>(g.ln_stats) + (long long)row * g.ln_np;
+  float s = 0.f, q = 0.f;
+  for (int p = 0; p < g.ln_np; ++p) { const float2 v = sp[p]; s += v.x; q += v.y; }
+  const float inv_k = 1.0f / (float)g.K;
+  mean = s * inv_k;
+  rstd = rsqrtf(fmaxf(q * inv_k - mean * mean, 0.f) + 1e-5f);
+}
+// r[i] <- rstd (r[i] - mean cs[i]) + bias[i] for the 32 columns of a chunk (thread = row); bias is applied here, not later
+__device__ __forceinline__ void ln_fold_chunk(uint32_t (&r)[32], float mean, float rstd, const float* cs, const float* bias) {
+  const float2 nm = make_float2(-mean, -mean), rs = make_float2(rstd, rstd);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 c = *reinterpret_cast<const float4*>(cs + i);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = *reinterpret_cast<const float4*>(bias + i);
+    float2 t0 = __ffma2_rn(nm, make_float2(c.x, c.y), make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+    float2 t1 = __ffma2_rn(nm, make_float2(c.z, c.w), make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+    t0 = __ffma2_rn(rs, t0, make_float2(b.x, b.y));
+    t1 = __ffma2_rn(rs, t1, make_float2(b.z, b.w));
+    r[i] = __float_as_uint(t0.x); r[i + 1] = __float_as_uint(t0.y); r[i + 2] = __float_as_uint(t1.x); r[i + 3] = __float_as_uint(t1.y);
+  }
+}
+
+// ---- transposed phase of the fp32 epilogues.  After the smem transpose lane l holds, for it = 0..7, columns (l%8)*4..+3 of
+// row it*4 + l/8 of the warp's 32 x 32 chunk: a warp-level access covers 4 rows x 128 contiguous bytes.
+template <int NIT>
+__device__ __forceinline__ void load_residual_rows(const GemmTcDev& g, int row_base, int n0, int lane, int it0, float4 (&res)[NIT]) {
+  const int cc = (lane & 7) * 4;
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int grow = row_base + (it0 + k) * 4 + (lane >> 3);
+    res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < g.M && n0 < g.N) {
+      const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
+      res[k] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+    }
+  }
+}
+// rows it0 .. it0+NIT-1 (per lane) of the chunk: stage (+ residual) -> C, bf16 copy, row statistics.  nxt_row_base >= 0: `res` is
+// refilled with the residual block of the chunk at (nxt_row_base, nxt_n0) as soon as it has been consumed, i.e. BEFORE this
+// chunk's stores are issued (the residual stream is updated in place, but a chunk's own columns are only read before they are
+// written).
+template <int NIT>
+__device__ __forceinline__ void epi_rows(const GemmTcDev& g, const float* stage, float2* rowacc, int row_base, int n0, int lane, int it0,
+                                         float4 (&res)[NIT], bool add_res, int nxt_row_base = -1, int nxt_n0 = 0) {
+  const int cc = (lane & 7) * 4;
+  float4 t[NIT];
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    t[k] = *reinterpret_cast<const float4*>(stage + ((it0 + k) * 4 + (lane >> 3)) * 36 + cc);
+    if (add_res) { t[k].x += res[k].x; t[k].y += res[k].y; t[k].z += res[k].z; t[k].w += res[k].w; }
+  }
+  if (nxt_row_base >= 0) load_residual_rows<NIT>(g, nxt_row_base, nxt_n0, lane, 0, res);
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int grow = row_base + (it0 + k) * 4 + (lane >> 3);
+    if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t[k];
+  }
+  // ---- this output feeds a LayerNorm: what the (folded) consumer needs is produced here, while the values are in registers
+  if (g.xb) {                                                     // bf16 copy of the rows: the next GEMM's A operand
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int grow = row_base + (it0 + k) * 4 + (lane >> 3);
+      if (grow < g.M)
+        *reinterpret_cast<uint2*>(g.xb + (long long)grow * g.ldxb + n0 + cc) = make_uint2(pack_bf16(t[k].x, t[k].y), pack_bf16(t[k].z, t[k].w));
+    }
+  }
+  if (rowacc) {
+    // per-row (sum, sum of squares) of this warp's column slice.  Each lane owns one slot per row it touches (row it*4 +
+    // lane/8, slot lane%8: 32 rows x 8 slots of float2, warp-private smem, conflict-free) and adds its 4 columns there;
+    // the 8 slots of a row are summed in a fixed order when the slice is complete - no shuffles on the way.
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      float2* a = rowacc + (it0 + k) * 32 + lane;
+      float2 acc = *a;
+      acc.x += (t[k].x + t[k].y) + (t[k].z + t[k].w);
+      acc.y = fmaf(t[k].x, t[k].x, fmaf(t[k].y, t[k].y, fmaf(t[k].z, t[k].z, fmaf(t[k].w, t[k].w, acc.y))));
+      *a = acc;
+    }
+  }
+}
 // `res` (optional): the residual block of THIS chunk, loaded by the caller ahead of time; it is refilled with the block at
 // (nxt_row_base, nxt_n0) before this chunk's stores are issued, so a residual read is always one chunk ahead of its use
 // (the residual stream is updated in place, but a chunk's own columns are only read before they are written).
 __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, bool row_ok, int n0, const uint32_t (&r)[32], int vb, int vtok,
                                                   const float* bias_chunk, float* stage = nullptr, int lane = 0, long long* tr2 = nullptr,
-                                                  float4 (*res_io)[8] = nullptr, int nxt_row_base = -1, int nxt_n0 = 0) {
+                                                  float4 (*res_io)[8] = nullptr, int nxt_row_base = -1, int nxt_n0 = 0,
+                                                  float2* rowacc = nullptr) {
   if (n0 >= g.N) return;
   if (stage != nullptr && (g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32)) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (g.bias) {
+    if (bias_chunk) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias_chunk + i);
@@ -89,23 +186,18 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     __syncwarp();
     const int row_base = row - lane;
-    const int cc = (lane & 7) * 4;
-    // all residual loads first (R aliases C for the in-place residual stream, so the compiler would otherwise
-    // serialise load -> add -> store per row and expose one memory latency per iteration)
-    float4 res_local[8];
-    float4 (&res)[8] = res_io ? *res_io : res_local;
-    if (g.epi == TC_EPI_F32_RES && !res_io) load_residual_chunk(g, row_base, n0, lane, res);
-    float4 t[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      t[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + (lane >> 3)) * 36 + cc);
-      if (g.epi == TC_EPI_F32_RES) { t[it].x += res[it].x; t[it].y += res[it].y; t[it].z += res[it].z; t[it].w += res[it].w; }
-    }
-    if (res_io && nxt_row_base >= 0) load_residual_chunk(g, nxt_row_base, nxt_n0, lane, res);
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int grow = row_base + it * 4 + (lane >> 3);
-      if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t[it];
+    if (res_io) {
+      // 8-warp kernel: the residual block of this chunk was loaded one chunk ahead (registers); refill it for the next chunk
+      // before this chunk's stores are issued
+      epi_rows<8>(g, stage, rowacc, row_base, n0, lane, 0, *res_io, true, nxt_row_base, nxt_n0);
+    } else {
+      // 16-warp kernel (96 registers): two halves of four rows-per-lane, residual loaded just in time - the other warps hide it
+#pragma unroll 1
+      for (int it0 = 0; it0 < 8; it0 += 4) {
+        float4 res4[4];
+        if (g.epi == TC_EPI_F32_RES) load_residual_rows<4>(g, row_base, n0, lane, it0, res4);
+        epi_rows<4>(g, stage, rowacc, row_base, n0, lane, it0, res4, g.epi == TC_EPI_F32_RES);
+      }
     }
     if (tr2) tr2[2] = clock64();
     __syncwarp();
@@ -121,7 +213,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
-      if (g.bias) {
+      if (bias_chunk) {
         const float4 b0 = *reinterpret_cast<const float4*>(bias_chunk + i);
         const float4 b1 = *reinterpret_cast<const float4*>(bias_chunk + i + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
@@ -136,7 +228,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (g.bias) {
+  if (bias_chunk) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(bias_chunk + i);
@@ -170,6 +262,40 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
   }
 }
 
+// bf16 output chunk (32 rows x 32 columns) through a warp-private smem box and ONE TMA store (SASS UTMASTG) instead of four
+// 16-byte stores per thread: a per-thread store instruction touches 32 different rows, i.e. 32 half-used sectors per request.
+// `stage`: 2 KB, 1024-byte aligned, laid out as the 64-byte-swizzled box the tensor map describes (16-byte chunk c of row r
+// sits at chunk c ^ ((r >> 1) & 3)), which also makes the warp's 16-byte smem writes bank-conflict free.
+__device__ __forceinline__ void tc_epilogue_chunk_bf16_tma(const GemmTcDev& g, const CUtensorMap* tmC, int row_base, int n0, const uint32_t (&r)[32],
+                                                           const float* bias_chunk, uint8_t* stage, int lane) {
+  if (n0 >= g.N) return;
+  if (lane == 0) tma_store_wait_read();                           // the previous box of this warp has left smem
+  __syncwarp();
+  uint8_t* my_row = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[i + e]);
+    if (bias_chunk) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_chunk + i);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_chunk + i + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (g.act == 1) gelu_erf_poly8(v);
+    *reinterpret_cast<uint4*>(my_row + (((i >> 3) ^ sw) << 4)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stage, n0, row_base);
+    tma_store_commit();
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
@@ -177,7 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_stage_area = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage_area + 8 * Cfg::WARP_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -259,20 +386,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
       const int row = m_blk * TC_BM + q * 32 + lane;
       const bool row_ok = row < g.M;
+      float* my_stage = reinterpret_cast<float*>(epi_stage_area + (warp - 2) * Cfg::WARP_STAGE_BYTES);
+      float2* rowacc = g.stats ? reinterpret_cast<float2*>(my_stage + 32 * 36) : nullptr;
+      if (rowacc) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rowacc[k * 32 + lane] = make_float2(0.f, 0.f);
+        __syncwarp();
+      }
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if (g.ln_stats) ln_row_scalars(g, row, row_ok, ln_mean, ln_rstd);        // while the tile's MMAs are still running
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       int vb = 0, vtok = 0;
       if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
+      const bool f32_out = g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32;
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
         tc_wait_ld();
         if (c0 + 32 == (chalf + 1) * (BN / 2)) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); }
-        tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? g.bias + n_blk * BN + c0 : nullptr);
+        const int n0 = n_blk * BN + c0;
+        const float* bias_chunk = g.bias ? g.bias + n0 : nullptr;
+        if (g.ln_stats && n0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, g.ln_colsum + n0, bias_chunk); bias_chunk = nullptr; }
+        tc_epilogue_chunk(g, row, row_ok, n0, r, vb, vtok, bias_chunk, f32_out ? my_stage : nullptr, lane, nullptr, nullptr, -1, 0, rowacc);
+      }
+      if (rowacc) {                                               // this warp's slice of the row statistics: partial p = 2 n_blk + chalf
+        __syncwarp();
+        if (row_ok && n_blk * BN + chalf * (BN / 2) < g.N) {
+          float2 a = rowacc[lane * 8];                            // this thread's row: slots lane*8 .. lane*8+7
+#pragma unroll
+          for (int k = 1; k < 8; ++k) { const float2 b = rowacc[lane * 8 + k]; a.x += b.x; a.y += b.y; }
+          reinterpret_cast<float2*>(g.stats)[(long long)row * g.stats_np + n_blk * 2 + chalf] = a;
+        }
       }
     }
   }
@@ -289,33 +438,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // of 48 KB for the same 128x256x64 MACs per SM; 5 pipeline stages + the epilogue staging fit.  The leader CTA (rank 0) owns the
 // `full` barriers (both CTAs' TMA bytes are signalled there) and issues every MMA; tcgen05.commit multicasts the
 // stage-free / accumulator-ready arrivals to both CTAs; each CTA's epilogue warps drain their own 128 TMEM lanes.
-constexpr int TC2_STAGES = 5;
 constexpr int TC2_STAGE_BYTES = 2 * TC_A_BYTES;                  // A 128x64 + W-half 128x64
 // EW = epilogue warps: 8 (two per TMEM lane quadrant, 128 columns each; fp32 outputs use a per-warp transpose tile) or
 // 16 (four per quadrant, 64 columns each) for the bf16 + GELU epilogue, whose per-tile latency with 8 warps (~13k
 // cycles) exceeds the tile's 10k MMA cycles at K = 1280.
-template <int EW> struct Tc2Cfg {
+// (A 16-warp / 3-stage variant of the fp32 residual epilogue was measured for the attention out-projection, which is bound by
+// its epilogue's memory traffic - 12 bytes per output element in 128-byte pieces spread over 128 rows - and was slower.)
+template <int EW, int STAGES> struct Tc2Cfg {
   static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int COLS = 256 / (EW / 4);                    // columns per epilogue warp
-  static constexpr int WARP_FLOATS = (EW == 8 ? 32 * 36 : 0) + COLS;   // transpose tile (8-warp kernel only) + bias slice
-  static constexpr int SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256 + EW * WARP_FLOATS * 4;
+  static constexpr bool F32_STAGE = EW == 8;                     // has the fp32 transpose tile + row-statistics slots
+  // per-warp epilogue staging, 1024-byte aligned: the fp32 transpose tile (32 x 36 floats; 8-warp kernel only), which doubles
+  // as the 2 KB bf16 box of the TMA-store epilogue
+  static constexpr int WARP_STAGE_BYTES = F32_STAGE ? 7168 : 2048;   // (+ 32 x 8 float2 row-statistics slots)
+  static constexpr int STAGE_AREA = EW * WARP_STAGE_BYTES;
+  static constexpr int BIAS_AREA = 2 * EW * COLS * 4;            // this warp's bias slice of the current tile + its LN column sums
+  static constexpr int SMEM_BYTES = STAGES * TC2_STAGE_BYTES + 1024 + STAGE_AREA + BIAS_AREA + 256;
 };
 
-template <int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<EW>::THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
+template <int EW, int TC2_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<EW, TC2_STAGES>::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const GemmTcDev g) {
   constexpr int BN = 256;
-  using Cfg2 = Tc2Cfg<EW>;
+  using Cfg2 = Tc2Cfg<EW, TC2_STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);
+  uint8_t* epi_stage_area = smem + TC2_STAGES * TC2_STAGE_BYTES;                       // 1024-byte aligned
+  float* epi_bias_area = reinterpret_cast<float*>(epi_stage_area + Cfg2::STAGE_AREA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage_area + Cfg2::STAGE_AREA + Cfg2::BIAS_AREA);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC2_STAGES;
   uint64_t* tmem_full = bars + 2 * TC2_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + TC2_STAGES * TC2_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -331,6 +488,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EW); }   // EW warps x 2 CTAs
     fence_mbar_init();
@@ -434,22 +592,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       // this warp's 128 bias values -> smem while the MMAs of the tile are still running
-      float* my_stage = epi_stage + (warp - 2) * Cfg2::WARP_FLOATS;
-      float* bias_s = my_stage + (EW == 8 ? 32 * 36 : 0);
-      if (g.bias && lane * 4 < COLS) {
+      float* my_stage = reinterpret_cast<float*>(epi_stage_area + (warp - 2) * Cfg2::WARP_STAGE_BYTES);
+      float* bias_s = epi_bias_area + (warp - 2) * 2 * COLS;
+      float* cs_s = bias_s + COLS;
+      if (lane * 4 < COLS) {
         const int nb = n_blk * BN + chalf * COLS + lane * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = b4;
+        if (g.bias && nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
+        if (g.ln_stats && nb < g.N) c4 = __ldg(reinterpret_cast<const float4*>(g.ln_colsum + nb));
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
+        *reinterpret_cast<float4*>(cs_s + lane * 4) = c4;
+      }
+      float2* rowacc = (Cfg2::F32_STAGE && g.stats) ? reinterpret_cast<float2*>(my_stage + 32 * 36) : nullptr;
+      if (rowacc) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rowacc[k * 32 + lane] = make_float2(0.f, 0.f);
       }
       __syncwarp();
+      const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if (g.ln_stats) ln_row_scalars(g, row, row_ok, ln_mean, ln_rstd);        // while the tile's MMAs are still running
       long long* tr = (g.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 24) ? g.trace + it * 8 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       if (tr) tr[1] = clock64();
-      const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
-      const bool row_ok = row < g.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       int vb = 0, vtok = 0;
       if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
@@ -465,6 +633,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         long long* tr2 = (tr && c0 == chalf * COLS + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
         if (tr2) tr2[3] = clock64();
+        const float* bias_chunk = g.bias ? bias_s + (c0 - chalf * COLS) : nullptr;
+        if (g.ln_stats && n_blk * BN + c0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, cs_s + (c0 - chalf * COLS), bias_chunk); bias_chunk = nullptr; }
         if (res_ahead) {
           int nrb = -1, nn0 = 0;
           if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
@@ -473,15 +643,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             nrb = (nt / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
             nn0 = (nt % n_tiles) * BN + chalf * COLS;
           }
-          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, my_stage, lane, tr2, &res, nrb, nn0);
+          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, my_stage, lane, tr2, &res, nrb, nn0, rowacc);
+        } else if (g.tma_store && (g.epi == TC_EPI_BF16 || n_blk * BN + c0 < 2 * g.D)) {
+          tc_epilogue_chunk_bf16_tma(g, &tmC, row - lane, n_blk * BN + c0, r, bias_chunk, reinterpret_cast<uint8_t*>(my_stage), lane);
         } else {
-          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, g.bias ? bias_s + (c0 - chalf * COLS) : nullptr, EW == 8 ? my_stage : nullptr, lane, tr2);
+          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, Cfg2::F32_STAGE ? my_stage : nullptr, lane, tr2, nullptr, -1, 0, rowacc);
         }
         if (tr) tr[2 + (c0 - chalf * COLS) / 32] = clock64();
+      }
+      if (rowacc) {                                               // this warp's slice of the row statistics: partial p = n_blk (BN / COLS) + chalf
+        __syncwarp();
+        if (row_ok && n_blk * BN + chalf * COLS < g.N) {
+          float2 a = rowacc[lane * 8];                            // this thread's row: slots lane*8 .. lane*8+7
+#pragma unroll
+          for (int k = 1; k < 8; ++k) { const float2 b = rowacc[lane * 8 + k]; a.x += b.x; a.y += b.y; }
+          reinterpret_cast<float2*>(g.stats)[(long long)row * g.stats_np + n_blk * (BN / COLS) + chalf] = a;
+        }
       }
     }
   }
 
+  if (g.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();     // bulk stores read this CTA's smem: drain before exit
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
@@ -513,6 +695,27 @@ static bool make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 output [rows, cols] with row stride ld: box = 32 cols x 32 rows, 64-byte swizzle (the epilogue's TMA store)
+static bool make_map_store(CUtensorMap* m, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int tma_store_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("WAT_GEMM_TMA_STORE");
+    mode = e ? (atoi(e) != 0) : 1;
+  }
+  return mode;
+}
+
 template <int BN>
 static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
@@ -523,9 +726,11 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, BN)) return cudaErrorInvalidValue;
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
-  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
+  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi; d.tma_store = 0;
   d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
   d.trace = nullptr;
+  d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
+  d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;
   const int m_tiles = (g.M + TC_BM - 1) / TC_BM, n_tiles = (g.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;
@@ -534,11 +739,11 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
 }
 
 
-template <int EW>
+template <int EW, int STAGES>
 static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
-  using Cfg2 = Tc2Cfg<EW>;
+  using Cfg2 = Tc2Cfg<EW, STAGES>;
   static unsigned long long attr_mask = 0;
-  if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW>, Cfg2::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW, STAGES>, Cfg2::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
   CUtensorMap tmA, tmB;
   if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, 128)) return cudaErrorInvalidValue;      // each CTA loads half of the 256 W rows
@@ -547,10 +752,20 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
   d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
   d.trace = g.trace;
+  d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
+  d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;
+  // bf16 outputs (fc1, the q | k part of QKV) are written by TMA from a smem box; needs a 16-byte aligned, 16-byte pitched C
+  CUtensorMap tmC = tmA;
+  d.tma_store = 0;
+  if (tma_store_mode() && (g.epi == TC_EPI_BF16 || g.epi == TC_EPI_QKV) && (g.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) {
+    const uint64_t c_cols = g.epi == TC_EPI_QKV ? 2 * (uint64_t)(g.N / 3) : (uint64_t)g.N;
+    if (!make_map_store(&tmC, g.C, g.M, c_cols, g.ldc)) return cudaErrorInvalidValue;
+    d.tma_store = 1;
+  }
   const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   int clusters = num_sms / 2;
   if (clusters > total) clusters = total;
-  gemm_tc2_kernel<EW><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, d);
+  gemm_tc2_kernel<EW, STAGES><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, d);
   return cudaGetLastError();
 }
 
@@ -564,15 +779,31 @@ static int pair_mode() {
   return mode;
 }
 
+static bool use_pair_kernel(int M, int N, int force_pair) {
+  return N % 256 == 0 && (force_pair > 0 || (force_pair == 0 && pair_mode() && M >= 256));
+}
+// number of per-row statistics slices a launch with GemmTc::stats set writes: one per epilogue warp column slice of the
+// kernel that will run (two per N tile)
+int gemm_tc_stats_slices(int M, int N, int K, int epi, int force_pair) {
+  (void)K; (void)epi;
+  if (use_pair_kernel(M, N, force_pair) || N % 256 == 0) return 2 * (N / 256);
+  return 2 * (N / 128);
+}
+
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   if (g.M <= 0) return cudaSuccess;
+  const bool f32_out = g.epi == TC_EPI_F32_RES || g.epi == TC_EPI_F32;
+  if ((g.xb || g.stats) && !f32_out) return cudaErrorInvalidValue;                     // producer extras live in the fp32 epilogues
+  if (g.stats && g.stats_np != gemm_tc_stats_slices(g.M, g.N, g.K, g.epi, g.force_pair)) return cudaErrorInvalidValue;
+  if (g.xb && (g.ldxb & 3)) return cudaErrorInvalidValue;
+  if (g.ln_stats && (!g.ln_colsum || g.ln_np <= 0)) return cudaErrorInvalidValue;
   if ((g.K & 7) || (g.lda & 7) || (g.N & 31) || (g.ldc & 7)) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return cudaErrorInvalidValue;
   if (g.epi == TC_EPI_QKV && ((g.N % 3) || ((g.N / 3) & 63) || g.seq_T <= 0)) return cudaErrorInvalidValue;
-  if (g.N % 256 == 0 && (g.force_pair > 0 || (g.force_pair == 0 && pair_mode() && g.M >= 256))) {
+  if (use_pair_kernel(g.M, g.N, g.force_pair)) {
     static const int wide = getenv("WAT_GEMM_EW16") ? atoi(getenv("WAT_GEMM_EW16")) : 1;
-    if (wide && g.epi == TC_EPI_BF16 && g.act == 1) return launch_tc2<16>(g, num_sms, st);     // GELU epilogue
-    return launch_tc2<8>(g, num_sms, st);
+    if (wide && g.epi == TC_EPI_BF16 && g.act == 1) return launch_tc2<16, 5>(g, num_sms, st);     // GELU epilogue
+    return launch_tc2<8, 5>(g, num_sms, st);
   }
   if (g.N % 256 == 0) return launch_tc<256>(g, num_sms, st);
   if (g.N % 128 == 0) return launch_tc<128>(g, num_sms, st);

@@ -69,10 +69,14 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
                               int hd, cudaStream_t st);
 
 // mean over groups of `win` consecutive rows: x [n_groups*win, D] (row stride D) -> out row g at out + g*out_stride
+// optional xb [n_groups, D] bf16 + stats [n_groups, 1, 2]: the row's bf16 copy and (sum, sum of squares) for a folded LayerNorm
 cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride,
-                              cudaStream_t st);
+                              cudaStream_t st, __nv_bfloat16* xb = nullptr, float* stats = nullptr);
 // encoder pooling: x [B, 1500, D] -> pooled[b, layer, 0..74, :] with pooled laid out [B, L, 75, D]
 cudaError_t launch_pool20(const float* x, int B, int T, int D, int layer, int L, float* pooled, cudaStream_t st);
+// the same from the bf16 copy of the residual stream the fc2 epilogue leaves (bf16 mode): half the bytes; rows summed in fp32
+// in a fixed order, so a clip's pooled state does not depend on its position in the batch
+cudaError_t launch_pool20_bf16(const __nv_bfloat16* xb, int B, int T, int D, int layer, int L, float* pooled, cudaStream_t st);
 
 // k=3, pad=1 im2col over time-major activations: src [B, Tin, C] -> out [B*Tout, 3C], row (b, j) =
 // (src[b, j*stride-1], src[b, j*stride], src[b, j*stride+1]) with zero rows outside [0, Tin)
@@ -84,9 +88,13 @@ cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n
 // TL-TR window regroup (model.py:360-367): pooled [B, L, Tp, D] -> rows (b, s, l, tau), zero rows past Tp
 // baseline heads: reduce the layer axis first (kind 0 = mean, 1 = last layer, 2 = weights w[L] / sum(w)); out rows = (b*S + s)*dw + tau
 cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                                     int kind, const float* w, float* out, cudaStream_t st);
+                                     int kind, const float* w, float* out, cudaStream_t st, __nv_bfloat16* xb = nullptr,
+                                     float* stats = nullptr);
 cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S,
-                               int D, float* out, cudaStream_t st);
+                               int D, float* out, cudaStream_t st, __nv_bfloat16* xb = nullptr, float* stats = nullptr);
+// W' = bf16(W diag(gamma)) [N, K], colsum [N], bias_out [N] = bias + W beta  (LayerNorm folded into the GEMM that consumes it)
+cudaError_t launch_fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                                   __nv_bfloat16* Wout, float* colsum, float* bias_out, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------- gemm_tc.cu (bf16 tcgen05)
 enum TcEpi : int {
@@ -106,8 +114,18 @@ struct GemmTc {
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head;  // flat row r -> (b = r / seq_T, t = r % seq_T)
   int force_pair;         // 0: default kernel choice, 1: CTA-pair kernel, -1: single-CTA kernel (tests)
   long long* trace;       // optional device buffer for a clock trace (tests)
+  // ---- LayerNorm folding (bf16 mode).  PRODUCER side, fp32 epilogues only (all optional): while the output rows are in
+  // registers the epilogue also writes
+  //   xb    [M, ldxb] bf16 copy of the rows (the next GEMM's A operand, un-normalised),
+  //   stats [M, stats_np, 2] fp32 (sum, sum of squares) per column slice; stats_np = gemm_tc_stats_slices(M, N, K, epi, force_pair).
+  __nv_bfloat16* xb; long long ldxb;
+  float* stats; int stats_np;
+  // CONSUMER side: A holds un-normalised rows; out = rstd (A W'^T - mean colsum) + bias with the rows' mean / rstd from
+  // ln_stats [M, ln_np, 2] and W', colsum, bias prepared by launch_fold_ln_weights
+  const float* ln_stats; int ln_np; const float* ln_colsum;
 };
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st);
+int gemm_tc_stats_slices(int M, int N, int K, int epi, int force_pair);
 
 // ---------------------------------------------------------------------------------- attn_tc.cu
 // V^T buffer: [B, H, VT_ROWS, Tpad] bf16 = V transposed per head (written by the QKV epilogue; K-major B operand of the

@@ -538,22 +538,48 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
 }
 
 // ------------------------------------------------------------------------------------------ means / pooling / regroup
-__global__ void group_mean_kernel(const float* __restrict__ x, int win, int D, float* __restrict__ out, long long out_stride) {
+// The row producers of the TL-TR head that are not GEMMs (window regroup, layer reduction, group mean) can also leave what a
+// LayerNorm folded into the next GEMM needs (gemm_tc.cu): the row's bf16 copy and its (sum, sum of squares) as ONE slice.
+// One 128-thread CTA per output row; RowTail collects the thread's share and reduces it in a fixed order.
+struct RowTail {
+  float s = 0.f, q = 0.f;
+  __device__ __forceinline__ void put(float4 v, int e, __nv_bfloat16* xb_row) {
+    s += (v.x + v.y) + (v.z + v.w);
+    q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+    if (xb_row) *reinterpret_cast<uint2*>(xb_row + e) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  __device__ __forceinline__ void finish(float2* stats_row) {      // every thread of the 128-thread CTA calls it
+    __shared__ float2 part[4];
+    const float ws = warp_sum(s), wq = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = make_float2(ws, wq);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      *stats_row = make_float2((part[0].x + part[1].x) + (part[2].x + part[3].x), (part[0].y + part[1].y) + (part[2].y + part[3].y));
+  }
+};
+
+__global__ void __launch_bounds__(128) group_mean_kernel(const float* __restrict__ x, int win, int D, float* __restrict__ out,
+                                                         long long out_stride, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   const int g = blockIdx.x;
   const float inv = 1.0f / (float)win;
+  RowTail tail;
   for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < win; ++r) {
       const float4 v = *reinterpret_cast<const float4*>(x + ((long long)g * win + r) * D + e);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
-    *reinterpret_cast<float4*>(out + (long long)g * out_stride + e) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    a = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    *reinterpret_cast<float4*>(out + (long long)g * out_stride + e) = a;
+    if (stats) tail.put(a, e, xb ? xb + (long long)g * D : nullptr);
   }
+  if (stats) tail.finish(stats + g);
 }
 
-cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride, cudaStream_t st) {
+cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride, cudaStream_t st,
+                              __nv_bfloat16* xb, float* stats) {
   if (n_groups <= 0) return cudaSuccess;
-  group_mean_kernel<<<n_groups, 128, 0, st>>>(x, win, D, out, out_stride);
+  group_mean_kernel<<<n_groups, 128, 0, st>>>(x, win, D, out, out_stride, xb, reinterpret_cast<float2*>(stats));
   return cudaGetLastError();
 }
 
@@ -579,8 +605,43 @@ cudaError_t launch_pool20(const float* x, int B, int T, int D, int layer, int L,
   return cudaGetLastError();
 }
 
-__global__ void head_gather_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
-                                   int S, int D, float* __restrict__ out) {
+// thread = 8 columns of one pooling window: 20 rows of 16-byte loads, all in flight before the first add
+__global__ void __launch_bounds__(160) pool20_bf16_kernel(const __nv_bfloat16* __restrict__ xb, int T, int D, int layer, int L,
+                                                          float* __restrict__ pooled) {
+  const int P = T / 20;
+  const int g = gridDim.x - 1 - blockIdx.x;                // walked from the end: the producer GEMM wrote the last rows last (L2)
+  const int b = g / P, w = g - b * P;
+  const __nv_bfloat16* src = xb + ((long long)b * T + (long long)w * 20) * D;
+  float* dst = pooled + (((long long)b * L + layer) * P + w) * D;
+  for (int e = threadIdx.x * 8; e < D; e += blockDim.x * 8) {
+    uint4 v[20];
+#pragma unroll
+    for (int r = 0; r < 20; ++r) v[r] = *reinterpret_cast<const uint4*>(src + (long long)r * D + e);
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 20; ++r) {
+      const uint32_t u[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[2 * k] += __uint_as_float(u[k] << 16);             // bf16 -> fp32 is a shift
+        a[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+      }
+    }
+    *reinterpret_cast<float4*>(dst + e) = make_float4(a[0] * 0.05f, a[1] * 0.05f, a[2] * 0.05f, a[3] * 0.05f);
+    *reinterpret_cast<float4*>(dst + e + 4) = make_float4(a[4] * 0.05f, a[5] * 0.05f, a[6] * 0.05f, a[7] * 0.05f);
+  }
+}
+
+cudaError_t launch_pool20_bf16(const __nv_bfloat16* xb, int B, int T, int D, int layer, int L, float* pooled, cudaStream_t st) {
+  if ((D & 7) || T % 20) return cudaErrorInvalidValue;
+  pool20_bf16_kernel<<<B * (T / 20), 160, 0, st>>>(xb, T, D, layer, L, pooled);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) head_gather_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
+                                   int S, int D, float* __restrict__ out, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   // out row = ((b*S + s)*L + l)*dw + tau
   long long r = blockIdx.x;
   const int tau = (int)(r % dw); r /= dw;
@@ -589,35 +650,51 @@ __global__ void head_gather_kernel(const float* __restrict__ pooled, int L, int 
   const int b = (int)(r / S);
   const int t = s * dw + tau;
   float* o = out + (long long)blockIdx.x * D;
+  __nv_bfloat16* xr = xb ? xb + (long long)blockIdx.x * D : nullptr;
+  RowTail tail;
   if (t < Tp) {
     const float* src = pooled + (((long long)b * L + l) * Tp_total + t_start + t) * D;
-    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4)
-      *reinterpret_cast<float4*>(o + e) = *reinterpret_cast<const float4*>(src + e);
-  } else {
-    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + e);
+      *reinterpret_cast<float4*>(o + e) = v;
+      if (stats) tail.put(v, e, xr);
+    }
+  } else {                                                        // zero rows of a ragged last window: LN of zeros = beta
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+      *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (stats) tail.put(make_float4(0.f, 0.f, 0.f, 0.f), e, xr);
+    }
   }
+  if (stats) tail.finish(stats + blockIdx.x);
 }
 
 cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                               float* out, cudaStream_t st) {
+                               float* out, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
   const long long rows = (long long)B * S * L * dw;
   if (rows <= 0) return cudaSuccess;
-  head_gather_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, out);
+  head_gather_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, out, xb, reinterpret_cast<float2*>(stats));
   return cudaGetLastError();
 }
 
 // Layer reduction of the baseline heads (models.py:113-167): mean over layers, last layer, or the learned layer weights
 // divided by their sum; rows of a ragged last window are zero like head_gather's.
-__global__ void head_layer_reduce_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
-                                         int S, int D, int kind, const float* __restrict__ w, float* __restrict__ out) {
+__global__ void __launch_bounds__(128) head_layer_reduce_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
+                                         int S, int D, int kind, const float* __restrict__ w, float* __restrict__ out,
+                                         __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   long long r = blockIdx.x;
   const int tau = (int)(r % dw); r /= dw;
   const int s = (int)(r % S);
   const int b = (int)(r / S);
   const int t = s * dw + tau;
   float* o = out + (long long)blockIdx.x * D;
+  __nv_bfloat16* xr = xb ? xb + (long long)blockIdx.x * D : nullptr;
+  RowTail tail;
   if (t >= Tp) {
-    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
+      *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (stats) tail.put(make_float4(0.f, 0.f, 0.f, 0.f), e, xr);
+    }
+    if (stats) tail.finish(stats + blockIdx.x);
     return;
   }
   const float* src = pooled + ((long long)b * L * Tp_total + t_start + t) * D;
@@ -638,15 +715,18 @@ __global__ void head_layer_reduce_kernel(const float* __restrict__ pooled, int L
       a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
     }
     *reinterpret_cast<float4*>(o + e) = a;
+    if (stats) tail.put(a, e, xr);
   }
+  if (stats) tail.finish(stats + blockIdx.x);
 }
 
 cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                                     int kind, const float* w, float* out, cudaStream_t st) {
+                                     int kind, const float* w, float* out, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
   const long long rows = (long long)B * S * dw;
   if (rows <= 0) return cudaSuccess;
   if (kind == 2 && !w) return cudaErrorInvalidValue;
-  head_layer_reduce_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, out);
+  head_layer_reduce_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, out, xb,
+                                                          reinterpret_cast<float2*>(stats));
   return cudaGetLastError();
 }
 
@@ -668,6 +748,35 @@ cudaError_t launch_im2col_k3(const void* src, bool bf16, int B, int Tin, int C, 
   const int per16 = bf16 ? 8 : 4;
   if (C % per16) return cudaErrorInvalidValue;
   im2col_k3_kernel<<<(unsigned)((long long)B * Tout), 128, 0, st>>>((const uint4*)src, Tin, C / per16, stride, Tout, (uint4*)out);
+  return cudaGetLastError();
+}
+
+// LayerNorm folded into the consuming GEMM (gemm_tc.cu): W' = bf16(W diag(gamma)), colsum[n] = sum_k W'[n,k] (of the ROUNDED
+// values: it cancels against the same products in the GEMM), bias_out[n] = bias[n] + sum_k W[n,k] beta[k].  Warp per row n.
+__global__ void __launch_bounds__(256) fold_ln_weights_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                                                              __nv_bfloat16* __restrict__ Wout, float* __restrict__ colsum,
+                                                              float* __restrict__ bias_out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(long long)n * K + k];
+    const __nv_bfloat16 wg = __float2bfloat16_rn(w * gamma[k]);
+    Wout[(long long)n * K + k] = wg;
+    cs += __bfloat162float(wg);
+    bs = fmaf(w, beta[k], bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) { colsum[n] = cs; bias_out[n] = (bias ? bias[n] : 0.f) + bs; }
+}
+
+cudaError_t launch_fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                                   __nv_bfloat16* Wout, float* colsum, float* bias_out, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  fold_ln_weights_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, gamma, beta, bias, N, K, Wout, colsum, bias_out);
   return cudaGetLastError();
 }
 

@@ -79,6 +79,9 @@ struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *b1, *b2;
   float *wqkv, *wo, *w1, *w2;                       // fp32 [3D,D] [D,D] [4D,D] [D,4D]
   __nv_bfloat16 *wqkv_h = nullptr, *wo_h = nullptr, *w1_h = nullptr, *w2_h = nullptr;
+  // bf16 mode: the two LayerNorms are folded into the GEMMs that consume them (gemm_tc.cu): wqkv_h = bf16(Wqkv diag(ln1_g)),
+  // w1_h = bf16(W1 diag(ln2_g)), with their column sums and the biases that absorb W beta
+  float *cs_qkv = nullptr, *bqkv_f = nullptr, *cs_1 = nullptr, *b1_f = nullptr;
 };
 
 struct Buf {
@@ -111,8 +114,13 @@ struct wat_handle {
   int ws_B = 0;
   int64_t rows_cap = 0;
   int head_chunk = 1;
-  Buf x, x2, xn, qkv, vt, att, hbuf, logspec, clipmax, melT, pooled, lmean, lnout, nvalid, logits, pcm_stage;
+  Buf x, x2, xn, qkv, vt, att, hbuf, logspec, clipmax, melT, pooled, lmean, lnout, nvalid, logits, pcm_stage, stats;
   cudaStream_t own_stream = nullptr;
+  // the workspace is shared by every call on the handle: when a call arrives on another stream than the previous one (e.g.
+  // wat_tag on the caller's stream, then wat_tag_host on the handle's own stream) it is ordered after the previous call's work
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
+  cudaEvent_t order_ev = nullptr;
   cudaStream_t copy_stream = nullptr;                            // wat_tag_host: H2D of PCM pieces, overlapped with the mel kernel
   cudaEvent_t piece_ev[8] = {};
   int64_t ws_bytes = 0;
@@ -311,9 +319,11 @@ int to_bf16(wat_handle* h, const float* src, __nv_bfloat16** dst, int64_t n) {
 int pack_block_bf16(wat_handle* h, BlockW& b) {
   const int64_t D = b.D;
   int rc;
-  if ((rc = to_bf16(h, b.wqkv, &b.wqkv_h, 3 * D * D))) return rc;
+  if ((rc = dalloc(h, &b.wqkv_h, 3 * D * D)) || (rc = dalloc(h, &b.cs_qkv, 3 * D)) || (rc = dalloc(h, &b.bqkv_f, 3 * D))) return rc;
+  KL(h, launch_fold_ln_weights(b.wqkv, b.ln1_g, b.ln1_b, b.bqkv, (int)(3 * D), (int)D, b.wqkv_h, b.cs_qkv, b.bqkv_f, 0));
   if ((rc = to_bf16(h, b.wo, &b.wo_h, D * D))) return rc;
-  if ((rc = to_bf16(h, b.w1, &b.w1_h, 4 * D * D))) return rc;
+  if ((rc = dalloc(h, &b.w1_h, 4 * D * D)) || (rc = dalloc(h, &b.cs_1, 4 * D)) || (rc = dalloc(h, &b.b1_f, 4 * D))) return rc;
+  KL(h, launch_fold_ln_weights(b.w1, b.ln2_g, b.ln2_b, b.b1, (int)(4 * D), (int)D, b.w1_h, b.cs_1, b.b1_f, 0));
   if ((rc = to_bf16(h, b.w2, &b.w2_h, 4 * D * D))) return rc;
   return 0;
 }
@@ -338,6 +348,10 @@ int ensure_ws(wat_handle* h, int B) {
   // hbuf also holds the conv1 im2col rows [Bc*3000, 3*n_mels], which exceed rows*4d when d < 1.5 n_mels
   const int64_t hbuf_elems = std::max(rows_cap * 4 * d, h->head_only ? (int64_t)0 : (int64_t)Bc * 3000 * 3 * h->cfg.n_mels);
   if ((rc = grow(h, h->hbuf, es * hbuf_elems))) return rc;
+  if (h->bf16) {                                                   // per-row (sum, sum of squares) slices for the folded LayerNorms
+    const int64_t np_max = std::max<int64_t>(std::max(d, (int64_t)h->di) / 64, 1);
+    if ((rc = grow(h, h->stats, sizeof(float) * 2 * rows_cap * np_max))) return rc;
+  }
   if (h->bf16 && !h->head_only) {
     if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;   // zeroed: the 36 padding keys stay 0
   }
@@ -375,40 +389,83 @@ int gemm(wat_handle* h, const void* A, int64_t lda, const float* Wf, const __nv_
   return 0;
 }
 
-// ResidualAttentionBlock.forward (model.py:128-139) on the fp32 residual stream x [n_seq*T, D]
-int run_block(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st,
-              float* pooled = nullptr, int pool_layer = -1) {
+// ResidualAttentionBlock.forward (model.py:128-139) on the fp32 residual stream x [n_seq*T, D]: fp32 mode (SIMT kernels)
+int run_block_f32(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st,
+                  float* pooled = nullptr, int pool_layer = -1) {
   const int D = w.D, rows = n_seq * T;
   int rc;
   // the first LayerNorm also emits the 20x pooled state of the PREVIOUS layer's output (= this block's input)
-  if (pooled && pool_layer >= 0) KL(h, launch_layernorm_pool20(x, w.ln1_g, w.ln1_b, n_seq, T, D, h->xn.p, h->bf16, pooled, pool_layer, h->L, st));
-  else KL(h, launch_layernorm(x, w.ln1_g, w.ln1_b, rows, D, h->xn.p, h->bf16, st));
+  if (pooled && pool_layer >= 0) KL(h, launch_layernorm_pool20(x, w.ln1_g, w.ln1_b, n_seq, T, D, h->xn.p, false, pooled, pool_layer, h->L, st));
+  else KL(h, launch_layernorm(x, w.ln1_g, w.ln1_b, rows, D, h->xn.p, false, st));
   if (encoder) h->prof_override = PC_GEMM_QKV;
-  if (h->bf16 && encoder) {
-    GemmTc g;
-    memset(&g, 0, sizeof(g));
-    g.A = (const __nv_bfloat16*)h->xn.p; g.lda = D; g.W = w.wqkv_h; g.bias = w.bqkv; g.C = h->qkv.p; g.ldc = 2 * D;
-    g.M = rows; g.N = 3 * D; g.K = D; g.epi = TC_EPI_QKV;
-    g.vt = (__nv_bfloat16*)h->vt.p; g.seq_T = T; g.seq_Tpad = 1536; g.n_head = w.H;
-    KL(h, launch_gemm_tc(g, h->num_sms, st));
-    KL(h, launch_attn_tc((const __nv_bfloat16*)h->qkv.p, (const __nv_bfloat16*)h->vt.p, (__nv_bfloat16*)h->att.p, n_seq, T,
-                         1536, w.H, st));
+  if ((rc = gemm(h, h->xn.p, D, w.wqkv, w.wqkv_h, w.bqkv, h->qkv.p, 3 * D, nullptr, 0, 0, rows, 3 * D, D, 0, false, st))) return rc;
+  if (encoder) {
+    const float* q = (const float*)h->qkv.p;
+    KL(h, launch_attn_f32_hd64(q, q + D, q + 2 * D, 3 * D, (float*)h->att.p, D, n_seq, T, w.H, st));
   } else {
-    if ((rc = gemm(h, h->xn.p, D, w.wqkv, w.wqkv_h, w.bqkv, h->qkv.p, 3 * D, nullptr, 0, 0, rows, 3 * D, D, 0, false, st))) return rc;
-    if (encoder) {
-      const float* q = (const float*)h->qkv.p;
-      KL(h, launch_attn_f32_hd64(q, q + D, q + 2 * D, 3 * D, (float*)h->att.p, D, n_seq, T, w.H, st));
-    } else {
-      KL(h, launch_attn_small(h->qkv.p, h->bf16, h->att.p, h->bf16, n_seq, T, w.H, D / w.H, st));
-    }
+    KL(h, launch_attn_small(h->qkv.p, false, h->att.p, false, n_seq, T, w.H, D / w.H, st));
   }
   if (encoder) h->prof_override = PC_GEMM_OUT;
   if ((rc = gemm(h, h->att.p, D, w.wo, w.wo_h, w.bo, x, D, x, D, 0, rows, D, D, 0, true, st))) return rc;
-  KL(h, launch_layernorm(x, w.ln2_g, w.ln2_b, rows, D, h->xn.p, h->bf16, st));
+  KL(h, launch_layernorm(x, w.ln2_g, w.ln2_b, rows, D, h->xn.p, false, st));
   if (encoder) h->prof_override = PC_GEMM_FC1;
   if ((rc = gemm(h, h->xn.p, D, w.w1, w.w1_h, w.b1, h->hbuf.p, 4 * D, nullptr, 0, 0, rows, 4 * D, D, 1, false, st))) return rc;
   if (encoder) h->prof_override = PC_GEMM_FC2;
   if ((rc = gemm(h, h->hbuf.p, 4 * D, w.w2, w.w2_h, w.b2, x, D, x, D, 0, rows, D, 4 * D, 0, true, st))) return rc;
+  return 0;
+}
+
+// fp32-output GEMM of the bf16 path whose output rows feed a LayerNorm: besides C (= R + act(A W^T + bias)) the epilogue
+// leaves the rows' bf16 copy in h->xn and their (sum, sum of squares) slices in h->stats; returns the slice count in *np
+int gemm_producer(wat_handle* h, const void* A, int64_t lda, const __nv_bfloat16* W, const float* bias, float* C, const float* R,
+                  int64_t ldr, int r_mod, int M, int N, int K, int act, cudaStream_t st, int* np) {
+  GemmTc g;
+  memset(&g, 0, sizeof(g));
+  g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = N; g.R = R; g.ldr = ldr; g.r_mod = r_mod;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.epi = R ? TC_EPI_F32_RES : TC_EPI_F32;
+  g.xb = (__nv_bfloat16*)h->xn.p; g.ldxb = N;
+  g.stats = (float*)h->stats.p; g.stats_np = gemm_tc_stats_slices(M, N, K, g.epi, 0);
+  *np = g.stats_np;
+  KL(h, launch_gemm_tc(g, h->num_sms, st));
+  return 0;
+}
+
+// The same block in bf16 mode.  No LayerNorm kernel runs: x arrives with its bf16 copy in h->xn and `np` statistics slices in
+// h->stats (left by whatever produced x), both LayerNorms are folded into the QKV / fc1 GEMMs, and the out-proj / fc2
+// epilogues leave the same by-products for the next consumer.  An encoder layer's 20x pooled state (model.py:171-174) is taken
+// from the bf16 copy fc2 leaves (pool20_bf16_kernel).
+int run_block_bf16(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st, int* np,
+                   float* pooled = nullptr, int pool_layer = -1) {
+  const int D = w.D, rows = n_seq * T;
+  int rc;
+  GemmTc g;
+  memset(&g, 0, sizeof(g));
+  g.A = (const __nv_bfloat16*)h->xn.p; g.lda = D; g.W = w.wqkv_h; g.bias = w.bqkv_f; g.C = h->qkv.p;
+  g.M = rows; g.N = 3 * D; g.K = D;
+  g.ln_stats = (const float*)h->stats.p; g.ln_np = *np; g.ln_colsum = w.cs_qkv;
+  if (encoder) {
+    g.ldc = 2 * D; g.epi = TC_EPI_QKV;
+    g.vt = (__nv_bfloat16*)h->vt.p; g.seq_T = T; g.seq_Tpad = 1536; g.n_head = w.H;
+    h->prof_override = PC_GEMM_QKV;
+    KL(h, launch_gemm_tc(g, h->num_sms, st));
+    KL(h, launch_attn_tc((const __nv_bfloat16*)h->qkv.p, (const __nv_bfloat16*)h->vt.p, (__nv_bfloat16*)h->att.p, n_seq, T,
+                         1536, w.H, st));
+  } else {
+    g.ldc = 3 * D; g.epi = TC_EPI_BF16;
+    KL(h, launch_gemm_tc(g, h->num_sms, st));
+    KL(h, launch_attn_small(h->qkv.p, true, h->att.p, true, n_seq, T, w.H, D / w.H, st));
+  }
+  if (encoder) h->prof_override = PC_GEMM_OUT;
+  if ((rc = gemm_producer(h, h->att.p, D, w.wo_h, w.bo, x, x, D, 0, rows, D, D, 0, st, np))) return rc;
+  memset(&g, 0, sizeof(g));
+  g.A = (const __nv_bfloat16*)h->xn.p; g.lda = D; g.W = w.w1_h; g.bias = w.b1_f; g.C = h->hbuf.p; g.ldc = 4 * D;
+  g.M = rows; g.N = 4 * D; g.K = D; g.act = 1; g.epi = TC_EPI_BF16;
+  g.ln_stats = (const float*)h->stats.p; g.ln_np = *np; g.ln_colsum = w.cs_1;
+  if (encoder) h->prof_override = PC_GEMM_FC1;
+  KL(h, launch_gemm_tc(g, h->num_sms, st));
+  if (encoder) h->prof_override = PC_GEMM_FC2;
+  if ((rc = gemm_producer(h, h->hbuf.p, 4 * D, w.w2_h, w.b2, x, x, D, 0, rows, D, 4 * D, 0, st, np))) return rc;
+  if (pooled && pool_layer >= 0) KL(h, launch_pool20_bf16((const __nv_bfloat16*)h->xn.p, n_seq, T, D, pool_layer, h->L, pooled, st));
   return 0;
 }
 
@@ -423,11 +480,18 @@ int run_encoder(wat_handle* h, int B, float* pooled, float* x_out, cudaStream_t 
                  false, st))) return rc;
   // conv2 (k3, s2, p1) + GELU + positional embedding : im2col [B*1500, 3d] -> x [B*1500, d] fp32
   KL(h, launch_im2col_k3(h->qkv.p, h->bf16, B, 3000, d, 2, 1500, h->hbuf.p, st));
-  if ((rc = gemm(h, h->hbuf.p, 3 * d, h->conv2_w, h->conv2_w_h, h->conv2_b, x, d, h->pos, d, 1500, B * 1500, d, 3 * d, 1, true, st)))
-    return rc;
-  for (int l = 0; l < h->L; ++l)
-    if ((rc = run_block(h, h->enc[l], x, B, 1500, true, st, pooled, l - 1))) return rc;
-  KL(h, launch_pool20(x, B, 1500, d, h->L - 1, h->L, pooled, st));   // last layer: nothing downstream reads x again
+  if (h->bf16) {
+    int np = 0;
+    if ((rc = gemm_producer(h, h->hbuf.p, 3 * d, h->conv2_w_h, h->conv2_b, x, h->pos, d, 1500, B * 1500, d, 3 * d, 1, st, &np))) return rc;
+    for (int l = 0; l < h->L; ++l)
+      if ((rc = run_block_bf16(h, h->enc[l], x, B, 1500, true, st, &np, pooled, l))) return rc;
+  } else {
+    if ((rc = gemm(h, h->hbuf.p, 3 * d, h->conv2_w, h->conv2_w_h, h->conv2_b, x, d, h->pos, d, 1500, B * 1500, d, 3 * d, 1, true, st)))
+      return rc;
+    for (int l = 0; l < h->L; ++l)
+      if ((rc = run_block_f32(h, h->enc[l], x, B, 1500, true, st, pooled, l - 1))) return rc;
+    KL(h, launch_pool20(x, B, 1500, d, h->L - 1, h->L, pooled, st));   // last layer: nothing downstream reads x again
+  }
   if (x_out) KL(h, launch_layernorm(x, h->lnp_g, h->lnp_b, B * 1500, d, x_out, false, st));
   return 0;
 }
@@ -452,23 +516,43 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
     const int rows = (int)(nb * rows_clip);
     const float* pin = pooled + (int64_t)b0 * L * t_total * d;
     float* src0 = head_has_down(mode) ? x2 : x;                   // regrouped input; the down-projection lands in x
+    // bf16 mode: whoever produces the rows a transformer block starts from also leaves their bf16 copy (h->xn) and their
+    // LayerNorm statistics (h->stats, `np` slices) - see run_block_bf16.  The down-projection's own LayerNorm stays a kernel.
+    const bool fold = h->bf16 && head_has_time_tr(mode);
+    const bool fold_src = fold && !head_has_down(mode);
+    __nv_bfloat16* xb = (__nv_bfloat16*)h->xn.p;
+    float* stats = (float*)h->stats.p;
+    int np = 1;
     if (layerwise) {
-      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, src0, st));
+      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, src0, st, fold_src ? xb : nullptr, fold_src ? stats : nullptr));
     } else {                                                      // baselines: the layer axis is reduced first (models.py:113-167)
       const int kind = (mode == WAT_HEAD_LAST_MLP || mode == WAT_HEAD_LAST_TR) ? 1 : head_has_layer_w(mode) ? 2 : 0;
-      KL(h, launch_head_layer_reduce(pin, nb, L, t_total, t_start, t_len, dw, S, d, kind, h->layer_w, src0, st));
+      KL(h, launch_head_layer_reduce(pin, nb, L, t_total, t_start, t_len, dw, S, d, kind, h->layer_w, src0, st,
+                                     fold_src ? xb : nullptr, fold_src ? stats : nullptr));
     }
     if (head_has_down(mode)) {
       KL(h, launch_layernorm(x2, h->down_g, h->down_b, rows, d, h->xn.p, h->bf16, st));
-      if ((rc = gemm(h, h->xn.p, d, h->down_w, h->down_w_h, h->down_bias, x, di, nullptr, 0, 0, rows, di, d, 0, true, st))) return rc;
+      if (h->bf16) {
+        if ((rc = gemm_producer(h, h->xn.p, d, h->down_w_h, h->down_bias, x, nullptr, 0, 0, rows, di, d, 0, st, &np))) return rc;
+      } else if ((rc = gemm(h, h->xn.p, d, h->down_w, h->down_w_h, h->down_bias, x, di, nullptr, 0, 0, rows, di, d, 0, true, st))) return rc;
     }
     if (layerwise) {
-      if ((rc = run_block(h, h->time_tr, x, nb * S * L, dw, false, st))) return rc;
-      KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st));
-      if ((rc = run_block(h, h->layer_tr, x2, nb * S, L, false, st))) return rc;
+      if (h->bf16) {
+        if ((rc = run_block_bf16(h, h->time_tr, x, nb * S * L, dw, false, st, &np))) return rc;
+        KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st, xb, stats));
+        np = 1;
+        if ((rc = run_block_bf16(h, h->layer_tr, x2, nb * S, L, false, st, &np))) return rc;
+      } else {
+        if ((rc = run_block_f32(h, h->time_tr, x, nb * S * L, dw, false, st))) return rc;
+        KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st));
+        if ((rc = run_block_f32(h, h->layer_tr, x2, nb * S, L, false, st))) return rc;
+      }
       KL(h, launch_group_mean(x2, nb * S, L, di, (float*)h->lmean.p, di, st));
     } else {
-      if (head_has_time_tr(mode) && (rc = run_block(h, h->time_tr, x, nb * S, dw, false, st))) return rc;
+      if (head_has_time_tr(mode)) {
+        if (h->bf16) { if ((rc = run_block_bf16(h, h->time_tr, x, nb * S, dw, false, st, &np))) return rc; }
+        else if ((rc = run_block_f32(h, h->time_tr, x, nb * S, dw, false, st))) return rc;
+      }
       KL(h, launch_group_mean(x, nb * S, dw, di, (float*)h->lmean.p, di, st));
     }
     KL(h, launch_layernorm((const float*)h->lmean.p, h->cls_g, h->cls_b, nb * S, di, h->lnout.p, false, st));
@@ -478,6 +562,20 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
     g.M = nb * S; g.N = nc; g.K = di; g.act = 0;
     KL(h, launch_gemm_f32(g, st));
   }
+  return 0;
+}
+
+// Calls on one handle are serialised on the device even when they come on different streams (they share the workspace).
+// The stream of the previous call must still exist (torch's streams live as long as the process).
+int order_after_previous(wat_handle* h, cudaStream_t st) {
+  if (h->last_stream_valid && h->last_stream != st) {
+    if (!h->order_ev) CU(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->order_ev, h->last_stream));
+    CU(cudaStreamWaitEvent(st, h->order_ev, 0));
+  }
+  h->last_stream = st;
+  h->last_stream_valid = true;
+  h->cur_stream = st;
   return 0;
 }
 
@@ -643,10 +741,11 @@ int wat_destroy(wat_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->owned) cudaFree(p);
   Buf* bufs[] = {&h->x, &h->x2, &h->xn, &h->qkv, &h->vt, &h->att, &h->hbuf, &h->logspec, &h->clipmax, &h->melT,
-                 &h->pooled, &h->lmean, &h->lnout, &h->nvalid, &h->logits, &h->pcm_stage};
+                 &h->pooled, &h->lmean, &h->lnout, &h->nvalid, &h->logits, &h->pcm_stage, &h->stats};
   for (Buf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   for (int i = 0; i < 8; ++i) if (h->piece_ev[i]) cudaEventDestroy(h->piece_ev[i]);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
@@ -661,7 +760,7 @@ int wat_logmel(wat_handle* h, const float* pcm, int64_t clip_stride, const int32
   int rc = 0;
   if (!pcm || !mel_out || B < 1 || n_samples < 1 || n_pad < 0 || n_frames < 1) return fail(WAT_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  h->cur_stream = st;
+  if ((rc = order_after_previous(h, st))) return rc;
   Buf &ls = h->logspec, &cm = h->clipmax, &nv = h->nvalid;
   if ((rc = grow(h, ls, sizeof(float) * (size_t)B * n_frames * h->cfg.n_mels))) return rc;
   if ((rc = grow(h, cm, sizeof(float) * B))) return rc;
@@ -678,7 +777,7 @@ int wat_encoder(wat_handle* h, const float* mel, int32_t B, float* pooled_out, f
   ON_DEVICE(h);
   if (!mel || !pooled_out || B < 1) return fail(WAT_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  h->cur_stream = st;
+  if ((rc = order_after_previous(h, st))) return rc;
   const int cb = h->cfg.max_batch;
   for (int b0 = 0; b0 < B; b0 += cb) {
     const int nb = std::min(cb, B - b0);
@@ -697,7 +796,7 @@ int wat_tltr(wat_handle* h, const float* pooled, int32_t B, int32_t t_total, int
   ON_DEVICE(h);
   if (!pooled || !logits_out || B < 1) return fail(WAT_ERR_INVALID, "bad argument");
   if ((rc = ensure_ws(h, std::min(B, h->cfg.max_batch)))) return rc;
-  h->cur_stream = (cudaStream_t)stream;
+  if ((rc = order_after_previous(h, (cudaStream_t)stream))) return rc;
   return run_head(h, pooled, B, t_total, t_start, t_len, dw, logits_out, (cudaStream_t)stream);
 }
 
@@ -755,7 +854,7 @@ static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_strid
   ON_DEVICE(h);
   if (!pcm || !logits_out || B < 1 || n_samples < 1 || n_samples > 480000) return fail(WAT_ERR_INVALID, "bad argument (clips are <= 480000 samples)");
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
-  h->cur_stream = st;
+  if ((rc = order_after_previous(h, st))) return rc;
   const int cb = h->cfg.max_batch;
   const int S = (75 + dw - 1) / dw;
   const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
@@ -943,6 +1042,46 @@ int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, 
   }
   cudaError_t e = launch_gemm_tc(g, sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "launch_gemm_tc: %s", cudaGetErrorString(e));
+  return WAT_OK;
+}
+
+// LayerNorm folded into its consumer, as run_block_bf16 chains it (all pointers device):
+//   producer  x = R + A1 W1^T + bias1            A1 [M,K1] bf16, W1 [D,K1] bf16, R / x [M,D] fp32; the epilogue also writes
+//             xb [M,D] bf16 and stats [M, np, 2] (np = return value of wat_dbg_ln_slices); if pooled != NULL (M % 1500 == 0),
+//             pooled [M/1500, 1, 75, D] = 20-row means of xb (pool20_bf16_kernel, as the encoder takes them)
+//   consumer  out [M,N2] bf16 = act(LN(x; gamma, beta) W2^T + bias2) computed as rstd (xb W2'^T - mean colsum) + bias2'
+// pair: 1 = CTA-pair kernels, -1 = single-CTA kernels.
+int wat_dbg_ln_slices(int32_t M, int32_t D, int32_t K1, int32_t pair) { return gemm_tc_stats_slices(M, D, K1, TC_EPI_F32_RES, pair); }
+int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const float* R, float* x, void* xb, float* stats, float* pooled,
+                    const float* W2, const float* gamma, const float* beta, const float* bias2, void* out, int32_t M, int32_t D,
+                    int32_t K1, int32_t N2, int32_t act, int32_t pair, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  __nv_bfloat16* W2h = nullptr;
+  float *cs = nullptr, *b2f = nullptr;
+  CU(cudaMalloc(&W2h, sizeof(__nv_bfloat16) * (size_t)N2 * D));
+  CU(cudaMalloc(&cs, sizeof(float) * N2));
+  CU(cudaMalloc(&b2f, sizeof(float) * N2));
+  cudaError_t e = launch_fold_ln_weights(W2, gamma, beta, bias2, N2, D, W2h, cs, b2f, st);
+  GemmTc g;
+  memset(&g, 0, sizeof(g));
+  g.A = (const __nv_bfloat16*)A1; g.lda = K1; g.W = (const __nv_bfloat16*)W1; g.bias = bias1; g.C = x; g.ldc = D; g.R = R; g.ldr = D;
+  g.M = M; g.N = D; g.K = K1; g.epi = TC_EPI_F32_RES; g.force_pair = pair;
+  g.xb = (__nv_bfloat16*)xb; g.ldxb = D; g.stats = stats; g.stats_np = gemm_tc_stats_slices(M, D, K1, TC_EPI_F32_RES, pair);
+  if (e == cudaSuccess) e = launch_gemm_tc(g, sms, st);
+  if (e == cudaSuccess && pooled) e = launch_pool20_bf16((const __nv_bfloat16*)xb, M / 1500, 1500, D, 0, 1, pooled, st);
+  GemmTc c;
+  memset(&c, 0, sizeof(c));
+  c.A = (const __nv_bfloat16*)xb; c.lda = D; c.W = W2h; c.bias = b2f; c.C = out; c.ldc = N2; c.M = M; c.N = N2; c.K = D; c.act = act;
+  c.epi = TC_EPI_BF16; c.force_pair = pair;
+  c.ln_stats = stats; c.ln_np = g.stats_np; c.ln_colsum = cs;
+  if (e == cudaSuccess) e = launch_gemm_tc(c, sms, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(W2h); cudaFree(cs); cudaFree(b2f);
+  if (e != cudaSuccess) return fail(WAT_ERR_CUDA, "ln gemm launch: %s", cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(WAT_ERR_CUDA, "ln gemm execution: %s", cudaGetErrorString(e2));
   return WAT_OK;
 }
 

@@ -64,6 +64,8 @@ _SIGS = {
     "wat_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "wat_dbg_gemm": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_gemm_bf16": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "wat_dbg_ln_slices": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "wat_dbg_ln_gemm": (C.c_int, [_fp] * 13 + [_i32] * 6 + [_vp]),
     "wat_dbg_attention": (C.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_tma_overlap_probe": (C.c_int, []),
 }
