@@ -175,6 +175,9 @@ WAT_API int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, 
 /* x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D]: fused-QKV GEMM + encoder self-attention (hd 64) */
 WAT_API int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
                       int32_t n_head, int32_t tc, void* stream);
+/* tc: 0 fp32 SIMT kernels, 1 tcgen05 kernels (max-free first pass + running-max fallback), 3 same with a clock trace on stderr,
+ * 4 tcgen05 with the running-max pass only.  wat_dbg_attention_repeats(): query tiles of the last call that fell back. */
+WAT_API int wat_dbg_attention_repeats(void);
 WAT_API int wat_dbg_tma_overlap_probe(void);   /* 1 if the driver accepts a tensor map whose row stride < row length */
 
 #ifdef __cplusplus

@@ -18,6 +18,18 @@
 // for every 64 keys): an SS-form M128 N64 K16 MMA reads 6 KB of operands for 32 cycles of math.  P in TMEM removes a
 // third of that traffic and the generic->async proxy fence.
 // K tail: 1500 = 23*64 + 28; TMA zero-fills rows >= T and those keys are excluded in the last tile only.
+//
+// Two passes.  The exponentials bind this kernel (head_dim 64: 128 MACs per exponential), and with them the softmax warps'
+// instruction count.  Pass 0 therefore runs the softmax WITHOUT a running maximum: q arrives pre-multiplied by
+// 64^-0.5 log2(e) (QKV epilogue), so P = 2^S directly - no row max, no subtraction, no rescale of O, no pv_done hand-shake for
+// it.  Every quantity is floating point (P bf16 with an 8-bit exponent, O and l fp32), so a common factor 2^-m is immaterial as
+// long as nothing leaves the exponent range: a row is accepted iff its sum l ends in [2^-100, 2^100] (that also catches inf
+// and NaN).  If any row of the tile fails, the CTA re-initialises its barriers and repeats the tile with the classic
+// online softmax (pass 1: running max with lazy rescale), whose result is the one written.  Scores of +-69 (natural units)
+// before the max is subtracted are far outside what Whisper produces, so pass 1 is the exception; it is what the unit tests
+// with inflated weights exercise.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -146,11 +158,67 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
   l += t.x + t.y;
 }
 
-template <bool TRACE>
+// Pass 0: P = 2^S with no reference maximum (see the header).  POLY selects which pairs of every 8 scores take the FMA-pipe
+// polynomial instead of MUFU.EX2: bit p of POLY = pair p (scores 2p, 2p+1) of the group; the pattern alternates between the low
+// and the high nibble on odd groups so that e.g. 0x31 gives 1 of 4 and 2 of 4 pairs in turn (37.5%).
+template <bool MASK, bool TRACE, int POLY>
+__device__ __forceinline__ void softmax_tile_fast(uint32_t tS, uint32_t tP, int nvalid, int j, int n_kv, AttnBars* bars, float& l,
+                                                  bool& s_next, long long* tr) {
+  uint32_t a[32], b[32];
+  tmem_ld32(tS, a);
+  tmem_ld32(tS + 32, b);
+  tc_wait_ld();
+  tc_fence_before();
+  mbar_arrive(&bars->s_free);                                     // S is in registers: Q K(j+1)^T may overwrite the buffer
+  AT_TRACE(0, j, 2);
+  float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0, ls2 = ls0, ls3 = ls0;
+  uint32_t pk[32];
+#pragma unroll
+  for (int g4 = 0; g4 < 8; ++g4) {
+    float p[8];
+    const int pat = (g4 & 1) ? (POLY >> 4) & 15 : POLY & 15;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      const int i = g4 * 8 + e;
+      const float2 x = make_float2(__uint_as_float(i < 32 ? a[i & 31] : b[i & 31]), __uint_as_float(i < 32 ? a[(i + 1) & 31] : b[(i + 1) & 31]));
+      if ((pat >> (e >> 1)) & 1) {
+        const float2 y = ex2_poly2_clamped(x);
+        p[e] = y.x;
+        p[e + 1] = y.y;
+      } else {
+        p[e] = ex2_approx(x.x);
+        p[e + 1] = ex2_approx(x.y);
+      }
+      if (MASK && i >= nvalid) p[e] = 0.f;
+      if (MASK && i + 1 >= nvalid) p[e + 1] = 0.f;
+    }
+    ls0 = __fadd2_rn(ls0, make_float2(p[0], p[1]));
+    ls1 = __fadd2_rn(ls1, make_float2(p[2], p[3]));
+    ls2 = __fadd2_rn(ls2, make_float2(p[4], p[5]));
+    ls3 = __fadd2_rn(ls3, make_float2(p[6], p[7]));
+    pk[g4 * 4 + 0] = pack_bf16(p[0], p[1]);
+    pk[g4 * 4 + 1] = pack_bf16(p[2], p[3]);
+    pk[g4 * 4 + 2] = pack_bf16(p[4], p[5]);
+    pk[g4 * 4 + 3] = pack_bf16(p[6], p[7]);
+  }
+  AT_TRACE(0, j, 4);
+  {
+    const bool okp = j > 0 ? mbar_test_wait(&bars->pv_done, (j - 1) & 1) : true;
+    s_next = j + 1 < n_kv ? mbar_test_wait(&bars->s_full, (j + 1) & 1) : true;
+    if (!okp) mbar_wait_spin(&bars->pv_done, (j - 1) & 1);
+    tc_fence_after();
+  }
+  tmem_st32(tP, pk);
+  tc_wait_st();
+  const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
+  l += t.x + t.y;
+}
+
+template <bool TRACE, int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
-               int q_tiles, float c_log2, long long* __restrict__ trace) {
+               int q_tiles, float c_log2, int first_pass, int ctrl, long long* __restrict__ trace, unsigned int* __restrict__ n_repeat) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -165,10 +233,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = bh % n_head, b = bh / n_head;
   const int n_kv = (T + AT_KV - 1) / AT_KV;
 
-  if (warp == 0 && lane == 0) {
+  // ctrl: which warp is the control warp (0 or 4); the other four are the softmax warps (TMEM lane quadrant = warp % 4)
+  const int first_sm = (ctrl + 1) % 5;
+  if (warp == ctrl && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmVT);
+  }
+  if (warp == first_sm) {
+    tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS);
+    tmem_alloc(&bars->tmem_slot_p, AT_TMEM_P_COLS);
+    tmem_relinquish();
+  }
+  __shared__ int s_bad;
+
+#pragma unroll 1
+  for (int pass = first_pass; pass < 2; ++pass) {
+  const bool fast = pass == 0;
+  if (warp == ctrl && lane == 0) {
+    if (pass > first_pass) {                                      // second pass of this tile: every phase of pass 0 has completed
+      mbar_inval(&bars->q_full);
+      for (int s = 0; s < AT_KSTAGE; ++s) mbar_inval(&bars->k_full[s]);
+      for (int s = 0; s < AT_NSTAGE; ++s) mbar_inval(&bars->v_full[s]);
+      mbar_inval(&bars->s_full); mbar_inval(&bars->p_full); mbar_inval(&bars->pv_done); mbar_inval(&bars->s_free);
+      if (n_repeat) atomicAdd(n_repeat, 1u);
+    }
+    s_bad = 0;
     mbar_init(&bars->q_full, 1);
     for (int s = 0; s < AT_KSTAGE; ++s) mbar_init(&bars->k_full[s], 1);
     for (int s = 0; s < AT_NSTAGE; ++s) mbar_init(&bars->v_full[s], 1);
@@ -191,18 +281,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     // and the first boxes of the tile that will follow this CTA on its SM slot (three CTAs per SM) go to L2
     const int nxt = blockIdx.x + 3 * AT_SMS;
-    if (nxt < (int)gridDim.x) {
+    if (pass == first_pass && nxt < (int)gridDim.x) {
       const int nqt = nxt % q_tiles, nbh = nxt / q_tiles, nh = nbh % n_head, nbb = nbh / n_head;
       tma_prefetch_l2_3d(&tmQ, nh * 64, nqt * 128, nbb);
       tma_prefetch_l2_3d(&tmK, D + nh * 64, 0, nbb);
       tma_prefetch_l2_3d(&tmK, D + nh * 64, AT_KV, nbb);
       tma_prefetch_l2_2d(&tmVT, 0, nbh * VT_ROWS);
     }
-  }
-  if (warp == 1) {
-    tmem_alloc(&bars->tmem_slot, AT_TMEM_COLS);
-    tmem_alloc(&bars->tmem_slot_p, AT_TMEM_P_COLS);
-    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
@@ -211,7 +296,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_O = tmem_base + 64;
   const uint32_t tmem_P = bars->tmem_slot_p;
 
-  if (warp == 0) {
+  if (warp == ctrl) {
     // Control warp: TMA producer and MMA issuer in one converged warp (only the elected lane issues).  Five warps per CTA
     // keep three CTAs on an SM at <= 4 warps per sub-partition, i.e. a 128-register budget for the softmax warps.
     // K(j+2) and V^T(j+1) are requested in the two issue blocks of step j (see the loop), K(0), K(1), V^T(0) and Q above.
@@ -286,7 +371,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 24), row sum
-    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && threadIdx.x == 32) ? trace : nullptr;
+    long long* tr = (trace && blockIdx.x == gridDim.x / 2 && warp == first_sm && lane == 0) ? trace : nullptr;
     bool s_ready = false;                                         // S(j) already seen complete by the previous step
     for (int j = 0; j < n_kv; ++j) {
       AT_TRACE(0, j, 0);
@@ -295,8 +380,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       AT_TRACE(0, j, 1);
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off;
-      if (nvalid >= AT_KV) softmax_tile<false, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, n_kv, bars, m_used, l, s_ready, tr);
-      else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
+      if (fast) {
+        if (nvalid >= AT_KV) softmax_tile_fast<false, TRACE, POLY>(tS, tmem_P + lane_off, AT_KV, j, n_kv, bars, l, s_ready, tr);
+        else softmax_tile_fast<true, TRACE, POLY>(tS, tmem_P + lane_off, nvalid, j, n_kv, bars, l, s_ready, tr);
+      } else {
+        if (nvalid >= AT_KV) softmax_tile<false, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, n_kv, bars, m_used, l, s_ready, tr);
+        else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
+      }
       AT_TRACE(0, j, 5);
       tc_fence_before();
       mbar_arrive(&bars->p_full);
@@ -304,6 +394,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_wait_spin(&bars->pv_done, (n_kv - 1) & 1);
     tc_fence_after();
+    // pass 0 is accepted iff every row sum stayed inside the exponent range (inf and NaN fail the comparisons too)
+    if (fast && !(l >= 7.888609052e-31f && l <= 1.267650600e30f)) s_bad = 1;
+    named_bar_sync(1, 128);                                       // the four softmax warps
+    if (!(fast && s_bad)) {
     const int tq = qt * 128 + r;
     __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;
     uint32_t v0[32], v1[32];
@@ -327,11 +421,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                        pack_bf16(__uint_as_float(v1[i + 4]) * inv, __uint_as_float(v1[i + 5]) * inv),
                        pack_bf16(__uint_as_float(v1[i + 6]) * inv, __uint_as_float(v1[i + 7]) * inv));
     }
+    }
+  }
+  // end of the pass: the control warp joins the softmax warps; a rejected pass 0 is repeated as pass 1
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (!(fast && s_bad)) break;
+  __syncthreads();                                                // everyone has read s_bad before it is cleared
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_P, AT_TMEM_P_COLS); tmem_dealloc(tmem_base, AT_TMEM_COLS); }
+  if (warp == first_sm) { tc_fence_after(); tmem_dealloc(bars->tmem_slot_p, AT_TMEM_P_COLS); tmem_dealloc(bars->tmem_slot, AT_TMEM_COLS); }
 }
 
 static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
@@ -344,11 +446,24 @@ static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuin
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int Tpad,
-                           int n_head, cudaStream_t st, long long* trace) {
+// POLY patterns of softmax_tile_fast (share of the exponentials evaluated on the FMA pipe): 0x11 = 25%, 0x31 = 37.5%, 0x33 = 50%
+template <int POLY>
+static cudaError_t launch_attn_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, __nv_bfloat16* out, int grid,
+                                       int T, int D, int n_head, int q_tiles, float c_log2, int first_pass, long long* trace,
+                                       unsigned int* n_repeat, cudaStream_t st) {
   static unsigned long long attr_mask = 0, attr_mask_tr = 0;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false, POLY>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true, POLY>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
+  static const int ctrl = getenv("WAT_ATTN_CTRL") ? atoi(getenv("WAT_ATTN_CTRL")) : 4;
+  if (trace) attn_tc_kernel<true, POLY><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, ctrl ? 4 : 0, trace, n_repeat);
+  else attn_tc_kernel<false, POLY><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, ctrl ? 4 : 0, nullptr, n_repeat);
+  return cudaGetLastError();
+}
+
+// q_prescaled: the q half of qk already carries the factor 64^-0.5 log2(e) (GemmTc::q_scale in the QKV epilogue); only then can
+// the max-free first pass run.  n_repeat (optional, device): incremented once per tile that had to be repeated with pass 1.
+cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T, int Tpad,
+                           int n_head, bool q_prescaled, cudaStream_t st, long long* trace, unsigned int* n_repeat) {
   const int D = n_head * 64;
   if (Tpad % AT_KV || Tpad < ((T + AT_KV - 1) / AT_KV) * AT_KV) return cudaErrorInvalidValue;
   CUtensorMap tmQ, tmK, tmVT;
@@ -366,10 +481,15 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
     if (!make_map_bf16(&tmVT, vt, 2, dims, strides, box)) return cudaErrorInvalidValue;
   }
   const int q_tiles = (T + 127) / 128;
-  const float c_log2 = 0.125f * 1.4426950408889634f;
-  if (trace) attn_tc_kernel<true><<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, trace);
-  else attn_tc_kernel<false><<<B * n_head * q_tiles, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, nullptr);
-  return cudaGetLastError();
+  const int grid = B * n_head * q_tiles;
+  const float c_log2 = q_prescaled ? 1.0f : AT_QSCALE;
+  static const int fast_on = getenv("WAT_ATTN_FAST") ? atoi(getenv("WAT_ATTN_FAST")) : 1;
+  static const int poly = getenv("WAT_ATTN_POLY") ? atoi(getenv("WAT_ATTN_POLY")) : 1;
+  const int first_pass = (fast_on && q_prescaled) ? 0 : 1;
+  if (poly == 0) return launch_attn_variant<0x11>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
+  if (poly == 2) return launch_attn_variant<0x33>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
+  if (poly == 3) return launch_attn_variant<0x00>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
+  return launch_attn_variant<0x31>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
 }
 
 }  // namespace wat

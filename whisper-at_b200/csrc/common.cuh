@@ -39,6 +39,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -335,6 +338,22 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   const float2 r = __fadd2_rn(x, magic);
   const float2 nf = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));
   const float2 f = __fadd2_rn(x, make_float2(-nf.x, -nf.y));
+  float2 p = __ffma2_rn(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.242611125f, 0.242611125f));
+  p = __ffma2_rn(p, f, make_float2(0.693260968f, 0.693260968f));
+  p = __ffma2_rn(p, f, make_float2(0.999928057f, 0.999928057f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
+}
+// The same for the attention fast path, where x is NOT bounded by a running max: x is first clamped to [-126, 128] by one
+// saturating FFMA per value (u = sat((x + 126) / 254), x_c = 254 u - 126), so 2^x_c never wraps the exponent field: x >= 128
+// gives inf / NaN (exponent 255) and x = 127 a finite 2^127, both of which the caller detects through the row sum.
+__device__ __forceinline__ float2 ex2_poly2_clamped(float2 x) {
+  const float ux = __saturatef(fmaf(x.x, 1.0f / 254.0f, 126.0f / 254.0f));
+  const float uy = __saturatef(fmaf(x.y, 1.0f / 254.0f, 126.0f / 254.0f));
+  const float2 u = make_float2(ux, uy), k254 = make_float2(254.0f, 254.0f);
+  const float2 r = __ffma2_rn(u, k254, make_float2(12582912.0f - 126.0f, 12582912.0f - 126.0f));    // x_c + 1.5 * 2^23: low bits = round(x_c)
+  const float2 n126 = __fadd2_rn(r, make_float2(-(12582912.0f - 126.0f), -(12582912.0f - 126.0f)));  // round(x_c) + 126
+  const float2 f = __ffma2_rn(u, k254, make_float2(-n126.x, -n126.y));                                // x_c - round(x_c)
   float2 p = __ffma2_rn(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.242611125f, 0.242611125f));
   p = __ffma2_rn(p, f, make_float2(0.693260968f, 0.693260968f));
   p = __ffma2_rn(p, f, make_float2(0.999928057f, 0.999928057f));

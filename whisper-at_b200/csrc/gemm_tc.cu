@@ -42,6 +42,7 @@ struct GemmTcDev {
   int M, N, K, act, epi;
   int tma_store;           // bf16 outputs leave through smem + TMA store (CTA-pair kernel)
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
+  float q_scale;           // QKV epilogue: q columns [0, D) are multiplied by it (0 = off)
   // fp32 epilogues as PRODUCER of the next LayerNorm (see kernels.h GemmTc): bf16 copy, per-slice row statistics
   __nv_bfloat16* xb; long long ldxb;
   float* stats; int stats_np;
@@ -208,6 +209,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
     // 8 columns at a time: bias, GELU, pack, one 16-byte store (keeps the live set small: this path also runs in the
     // 16-epilogue-warp kernel, which has ~96 registers per thread)
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.C) + (long long)row * g.ldc + n0;
+    const float qs = (g.epi == TC_EPI_QKV && g.q_scale != 0.f && n0 < g.D) ? g.q_scale : 1.0f;
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       float v[8];
@@ -220,6 +222,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
       if (g.act == 1) gelu_erf_poly8(v);
+      if (qs != 1.0f) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= qs;
+      }
       *reinterpret_cast<uint4*>(cp + i) =
           make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
@@ -273,6 +279,7 @@ __device__ __forceinline__ void tc_epilogue_chunk_bf16_tma(const GemmTcDev& g, c
   __syncwarp();
   uint8_t* my_row = stage + lane * 64;
   const int sw = (lane >> 1) & 3;
+  const float qs = (g.epi == TC_EPI_QKV && g.q_scale != 0.f && n0 < g.D) ? g.q_scale : 1.0f;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     float v[8];
@@ -285,6 +292,10 @@ __device__ __forceinline__ void tc_epilogue_chunk_bf16_tma(const GemmTcDev& g, c
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
     if (g.act == 1) gelu_erf_poly8(v);
+    if (qs != 1.0f) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= qs;
+    }
     *reinterpret_cast<uint4*>(my_row + (((i >> 3) ^ sw) << 4)) =
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
@@ -727,7 +738,7 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi; d.tma_store = 0;
-  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale;
   d.trace = nullptr;
   d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
   d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;
@@ -750,7 +761,7 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
-  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale;
   d.trace = g.trace;
   d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
   d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;

@@ -112,6 +112,7 @@ struct GemmTc {
   int M, N, K, act, epi;
   // TC_EPI_QKV only:
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head;  // flat row r -> (b = r / seq_T, t = r % seq_T)
+  float q_scale;          // TC_EPI_QKV: factor applied to the q columns [0, D) before rounding (0 = none)
   int force_pair;         // 0: default kernel choice, 1: CTA-pair kernel, -1: single-CTA kernel (tests)
   long long* trace;       // optional device buffer for a clock trace (tests)
   // ---- LayerNorm folding (bf16 mode).  PRODUCER side, fp32 epilogues only (all optional): while the output rows are in
@@ -133,8 +134,12 @@ int gemm_tc_stats_slices(int M, int N, int K, int epi, int force_pair);
 // the buffer is zeroed when it is allocated.
 constexpr int VT_ROWS = 64;
 // qk: [B*T, 2D] bf16 (q | k), vt as above, out: [B*T, D] bf16
+// q_prescaled: q already carries AT_QSCALE = 64^-0.5 log2(e) (GemmTc::q_scale), which enables the max-free first pass;
+// n_repeat: optional device counter of tiles that fell back to the running-max pass
+constexpr float AT_QSCALE = 0.125f * 1.4426950408889634f;
 cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int T,
-                           int Tpad, int n_head, cudaStream_t st, long long* trace = nullptr);
+                           int Tpad, int n_head, bool q_prescaled, cudaStream_t st, long long* trace = nullptr,
+                           unsigned int* n_repeat = nullptr);
 
 // driver entry point for cuTensorMapEncodeTiled, resolved once through the runtime
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -446,10 +446,11 @@ int run_block_bf16(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, b
   if (encoder) {
     g.ldc = 2 * D; g.epi = TC_EPI_QKV;
     g.vt = (__nv_bfloat16*)h->vt.p; g.seq_T = T; g.seq_Tpad = 1536; g.n_head = w.H;
+    g.q_scale = AT_QSCALE;                                        // q leaves the epilogue as q * 64^-0.5 * log2(e): attention computes P = 2^S
     h->prof_override = PC_GEMM_QKV;
     KL(h, launch_gemm_tc(g, h->num_sms, st));
     KL(h, launch_attn_tc((const __nv_bfloat16*)h->qkv.p, (const __nv_bfloat16*)h->vt.p, (__nv_bfloat16*)h->att.p, n_seq, T,
-                         1536, w.H, st));
+                         1536, w.H, true, st));
   } else {
     g.ldc = 3 * D; g.epi = TC_EPI_BF16;
     KL(h, launch_gemm_tc(g, h->num_sms, st));
@@ -1085,6 +1086,10 @@ int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const fl
   return WAT_OK;
 }
 
+// tiles of the last wat_dbg_attention(tc != 0) call that were repeated with the running-max pass
+static thread_local int g_dbg_attn_repeats = 0;
+int wat_dbg_attention_repeats(void) { return g_dbg_attn_repeats; }
+
 // x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D] fp32 = softmax(q k^T / 8) v per head (QKV GEMM + attention)
 int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
                       int32_t n_head, int32_t tc, void* stream) {
@@ -1121,10 +1126,21 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
   memset(&g, 0, sizeof(g));
   g.A = xh; g.lda = D; g.W = wh; g.bias = bqkv; g.C = qk; g.ldc = 2 * D; g.M = (int)rows; g.N = 3 * D; g.K = D;
   g.epi = TC_EPI_QKV; g.vt = vt; g.seq_T = T; g.seq_Tpad = Tpad; g.n_head = n_head;
+  g.q_scale = tc == 4 ? 0.f : AT_QSCALE;                          // tc 4: un-scaled q -> only the running-max pass can run
   cudaError_t e = launch_gemm_tc(g, sms, st);
   long long* trace = nullptr;
   if (tc == 3) { CU(cudaMalloc(&trace, 8192)); CU(cudaMemsetAsync(trace, 0, 8192, st)); }
-  if (e == cudaSuccess) e = launch_attn_tc(qk, vt, oh, B, T, Tpad, n_head, st, trace);
+  unsigned int* n_rep = nullptr;
+  CU(cudaMalloc(&n_rep, sizeof(unsigned int)));
+  CU(cudaMemsetAsync(n_rep, 0, sizeof(unsigned int), st));
+  if (e == cudaSuccess) e = launch_attn_tc(qk, vt, oh, B, T, Tpad, n_head, tc != 4, st, trace, n_rep);
+  {
+    unsigned int hr = 0;
+    cudaStreamSynchronize(st);
+    cudaMemcpy(&hr, n_rep, sizeof(hr), cudaMemcpyDeviceToHost);
+    cudaFree(n_rep);
+    g_dbg_attn_repeats = (int)hr;
+  }
   if (trace) {                                                    // per-phase clock trace of one CTA -> stderr
     long long ht[1024];
     cudaStreamSynchronize(st);
