@@ -330,12 +330,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (!okk) mbar_wait_spin(&bars->k_full[st ^ 1], phk);
         AT_TRACE(512, j, 5);
         if (!oks) mbar_wait_spin(&bars->s_free, j & 1);
+        AT_TRACE(512, j, 6);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dK = make_smem_desc_sw128(smem_u32(sK + (st ^ 1) * AT_K_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, dQ + 2 * k, dK + 2 * k, idesc, k != 0);
           umma_commit(&bars->s_full);
+          AT_TRACE(512, j, 7);
           if (j + 2 < n_kv) {
             mbar_expect_tx(&bars->k_full[st], AT_K_BYTES);
             tma_load_3d(sK + st * AT_K_BYTES, &tmK, &bars->k_full[st], D + h * 64, (j + 2) * AT_KV, b);

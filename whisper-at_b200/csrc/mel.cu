@@ -4,26 +4,28 @@
 //            -> |X|^2 -> sparse slaney mel projection -> log10(max(.,1e-10)), plus the per-clip maximum.
 //   phase 2  mel_norm_kernel  : max(x, clipmax - 8), (x + 4) / 4, written in the layout the consumer wants.
 //
-// The DFT is evaluated directly (no FFT) with fp64 accumulation over the twice-folded frame.  First fold (real input):
-//   Re X[k] = x[0] + (-1)^k x[200] + sum_{n=1..199} E[n] cos(2 pi n k / 400),   E[n] = x[n] + x[400-n]
-//   Im X[k] =                      - sum_{n=1..199} O[n] sin(2 pi n k / 400),   O[n] = x[n] - x[400-n]
-// second fold (n <-> 200-n, cos/sin pick up (-1)^k): for n = 1..99 only
-//   sum E cos = E[100] cos(pi k/2) + sum_n (E[n] + (-1)^k E[200-n]) cos(.),  sum O sin = O[100] sin(pi k/2) + sum_n (O[n] - (-1)^k O[200-n]) sin(.)
-// so every bin needs 2 x 99 DFMA instead of 2 x 199; even and odd bins read their own folded sequences.
-// so the result is the exact transform of the fp32 windowed frame (the reference's own fp32 FFT is
-// ~1e-5 away from it in log-mel units; SURVEY.md §7 "mel tolerance is tight").  Only bins 1..199 are
-// evaluated: columns 0 and 200 of the slaney filterbank are zero.
+// The 400-point DFT of a frame is a three-stage Cooley-Tukey transform, 400 = 16 x 5 x 5, evaluated in fp64 (what enters is
+// the fp32 product sample * window, exactly as torch.stft forms it, so the result is the exact transform of the reference's
+// windowed frame; the reference's own fp32 FFT sits ~1e-5 away from it in log-mel units - SURVEY.md §7 "mel tolerance is
+// tight").  With n = 25 n1 + n2 and k = k1 + 16 k2:
+//   A.  Y[n2][k1] = sum_n1 x[25 n1 + n2] W16^(n1 k1)       16-point DFT of a REAL sequence: only k1 = 0..8 are evaluated
+//       T[n2][k1] = Y[n2][k1] W400^(n2 k1)                  (four real 4-point DFTs + 3 complex MACs per k1)
+//   B.  X[k1 + 16 k2] = sum_n2 T[n2][k1] W25^(n2 k2)        25-point DFT as 5 x 5 (n2 = 5a + b, k2 = c + 5d):
+//       B1. Z[b][c] = W25^(bc) sum_a T[5a + b] W5^(ac)      in place (a thread owns the five slots of residue b)
+//       B2. X[c + 5d] = sum_b Z[b][c] W5^(bd)
+// Bins k with k mod 16 in 9..15 are never formed: |X[k]|^2 = |X[400 - k]|^2 for real input and (400 - k) mod 16 is in 1..7.
+// Only bins 1..199 are needed (columns 0 and 200 of the slaney filterbank are zero).  ~12.5k fp64 FMAs per frame instead of
+// the 39.6k (+ 50% twiddle rotations) of the twice-folded direct DFT this kernel used in round 1.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace wat {
 
-constexpr int MEL_F = 20;                          // frames per CTA
+constexpr int MEL_F = 10;                          // frames per CTA
 constexpr int MEL_THREADS = 256;
 constexpr int MEL_SPAN = MEL_F * 160 + 240;        // samples a CTA touches
 constexpr int MEL_BINS = 200;                      // bins 0..199 (200 has zero weight)
-
-struct __align__(16) EO { double e, o; };
+constexpr int MEL_K1 = 9;                          // k1 = 0..8 of the 16-point stage
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // monotone int encoding: works for mixed signs
@@ -31,8 +33,24 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, fma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {          // c + a b
+  return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+// out[c] = sum_a in[a] W5^(a c), W5^j = w5[j] (j = 0..4)
+__device__ __forceinline__ void dft5(const double2 (&in)[5], const double2 (&w5)[5], double2 (&out)[5]) {
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    double2 acc = in[0];
+#pragma unroll
+    for (int a = 1; a < 5; ++a) acc = cfma(in[a], w5[(a * c) % 5], acc);
+    out[c] = acc;
+  }
+}
+
 // grid: (ceil(n_frames/MEL_F), B).  logspec: [B, frames_alloc, n_mels] (frames >= n_store only feed the max)
-__global__ void __launch_bounds__(MEL_THREADS, 2)
+__global__ void __launch_bounds__(MEL_THREADS, 3)
 mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_stride, const int* __restrict__ n_valid_arr,
                  int n_valid_all, int n_pad, int n_frames, int n_store, int frames_alloc, int n_mels,
                  const double2* __restrict__ twiddle,      // [400] (cos, sin)(2 pi j / 400)
@@ -42,8 +60,9 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
                  const float* __restrict__ fb_w,           // packed non-zero weights
                  float* __restrict__ logspec, float* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  EO* eo = reinterpret_cast<EO*>(smem_raw);                               // [2 parities][MEL_F][100]
-  float* xs = reinterpret_cast<float*>(eo + 2 * MEL_F * 100);             // [MEL_SPAN]
+  double2* tw = reinterpret_cast<double2*>(smem_raw);                     // [400] W400^j = exp(-2 pi i j / 400)
+  double2* Tb = tw + 400;                                                 // [MEL_F][MEL_K1][25]
+  float* xs = reinterpret_cast<float*>(Tb + MEL_F * MEL_K1 * 25);         // [MEL_SPAN]
   float* pw = xs + MEL_SPAN;                                              // [MEL_F][MEL_BINS]
   __shared__ float s_max[MEL_THREADS / 32];
 
@@ -65,80 +84,71 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
     if (s >= 0 && s < n_valid) smp = pcm_i16 ? (float)__ldg(xi + s) * (1.0f / 32768.0f) : __ldg(xf + s);
     xs[i] = smp;
   }
-  __syncthreads();
-  // fold twice.  eo[(par * MEL_F + f) * 100 + n], n = 1..99: (E[n] +/- E[200-n], O[n] -/+ O[200-n]) for bins of parity par;
-  // slot n = 0 keeps the per-frame specials: par 0 -> (x[0] + x[200], E[100]);  par 1 -> (x[0] - x[200], O[100])
-  for (int i = tid; i < MEL_F * 100; i += MEL_THREADS) {
-    const int f = i / 100, n = i - f * 100;
-    const float* fr = xs + f * 160;
-    auto xw = [&](int j) { return (double)__fmul_rn(fr[j], window[j]); };
-    EO ev, od;
-    if (n == 0) {
-      const double x0 = xw(0), x200 = xw(200), a = xw(100), b = xw(300);
-      ev.e = x0 + x200; ev.o = a + b;                               // E[100]
-      od.e = x0 - x200; od.o = a - b;                               // O[100]
-    } else {
-      const double a = xw(n), b = xw(400 - n), c = xw(200 - n), d = xw(200 + n);
-      const double En = a + b, On = a - b, Em = c + d, Om = c - d;  // m = 200 - n
-      ev.e = En + Em; ev.o = On - Om;
-      od.e = En - Em; od.o = On + Om;
-    }
-    eo[(0 * MEL_F + f) * 100 + n] = ev;
-    eo[(1 * MEL_F + f) * 100 + n] = od;
-  }
+  for (int i = tid; i < 400; i += MEL_THREADS) { const double2 t = twiddle[i]; tw[i] = make_double2(t.x, -t.y); }
+  for (int i = tid; i < MEL_F; i += MEL_THREADS) pw[i * MEL_BINS] = 0.f;   // bin 0 is never formed (zero filter weight)
   __syncthreads();
 
-  // DFT: thread = 4 bins of one parity x 4 frames.  (25 even + 25 odd bin groups) x 5 frame groups = 250 threads.
-  if (tid < 250) {
-    const int bg = tid % 50, fg = tid / 50;
-    const int par = bg >= 25;
-    const int kbase = 8 * (bg - 25 * par) + par;                   // bins kbase, kbase+2, kbase+4, kbase+6
-    double re[4][4], im[4][4];
+  // ---- stage A: thread = (frame, n2): 16-point DFT over n1 of the real sequence x[25 n1 + n2], outputs k1 = 0..8
+  for (int item = tid; item < MEL_F * 25; item += MEL_THREADS) {
+    const int f = item / 25, n2 = item - f * 25;
+    const float* fr = xs + f * 160;
+    double e0[4], e2[4];                                                  // E_r[0], E_r[2] (real);  E_r[1] = (d0[r], -d1[r]), E_r[3] = conj
+    double d0[4], d1[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) { re[a][b] = 0.0; im[a][b] = 0.0; }
-    // twiddles w = e^(2 pi i n k / 400) by an fp64 rotation per step instead of a table gather: a gather over bins that
-    // are 8 apart puts every lane of a warp on the same shared-memory banks (25-way conflicts made this kernel 6x slower
-    // than its DFMA count); 99 rotations accumulate ~1e-14 of error, far below the fp32 inputs.
-    double2 w[4], r[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) { r[a] = twiddle[kbase + 2 * a]; w[a] = r[a]; }
-    const EO* base = eo + (par * MEL_F + fg * 4) * 100;
-    for (int n = 1; n < 100; ++n) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const EO v = base[b * 100 + n];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          re[a][b] = fma(v.e, w[a].x, re[a][b]);
-          im[a][b] = fma(v.o, w[a].y, im[a][b]);
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double wx = w[a].x * r[a].x - w[a].y * r[a].y;
-        w[a].y = fma(w[a].x, r[a].y, w[a].y * r[a].x);
-        w[a].x = wx;
-      }
+    for (int r = 0; r < 4; ++r) {                                         // real 4-point DFT of x[25 (4m + r) + n2], m = 0..3
+      const double x0 = (double)__fmul_rn(fr[25 * r + n2], window[25 * r + n2]);
+      const double x1 = (double)__fmul_rn(fr[25 * (r + 4) + n2], window[25 * (r + 4) + n2]);
+      const double x2 = (double)__fmul_rn(fr[25 * (r + 8) + n2], window[25 * (r + 8) + n2]);
+      const double x3 = (double)__fmul_rn(fr[25 * (r + 12) + n2], window[25 * (r + 12) + n2]);
+      const double sa = x0 + x2, sb = x1 + x3;
+      e0[r] = sa + sb; e2[r] = sa - sb; d0[r] = x0 - x2; d1[r] = x1 - x3;
     }
+    double2* dst = Tb + (f * MEL_K1) * 25 + n2;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const EO sp = base[b * 100];
+    for (int k1 = 0; k1 < MEL_K1; ++k1) {
+      const int q = k1 & 3;
+      double2 acc;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int k = kbase + 2 * a;
-        double r, i2;
-        if (!par) {                                                 // even k = 2m: cos(pi k/2) = (-1)^m, sin = 0
-          r = re[a][b] + sp.e + (((k >> 1) & 1) ? -sp.o : sp.o);
-          i2 = im[a][b];
-        } else {                                                    // odd k: cos = 0, sin(pi k/2) = (-1)^((k-1)/2)
-          r = re[a][b] + sp.e;
-          i2 = im[a][b] + ((((k - 1) >> 1) & 1) ? -sp.o : sp.o);
-        }
-        const double p = r * r + i2 * i2;
-        if (k < MEL_BINS) pw[(fg * 4 + b) * MEL_BINS + k] = (float)p;
+      for (int r = 0; r < 4; ++r) {
+        const double2 er = q == 0 ? make_double2(e0[r], 0.0) : q == 2 ? make_double2(e2[r], 0.0)
+                         : q == 1 ? make_double2(d0[r], -d1[r]) : make_double2(d0[r], d1[r]);
+        if (r == 0) acc = er;
+        else acc = cfma(er, tw[(25 * r * k1) % 400], acc);                 // W16^(r k1) = W400^(25 r k1)
       }
+      dst[k1 * 25] = cmul(acc, tw[n2 * k1]);
+    }
+  }
+  __syncthreads();
+  double2 w5[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) w5[j] = tw[80 * j];
+  // ---- stage B1: thread = (frame, k1, b): 5-point DFT over a of T[5a + b], times W25^(b c), in place
+  for (int item = tid; item < MEL_F * MEL_K1 * 5; item += MEL_THREADS) {
+    const int b = item % 5, fk = item / 5;
+    double2* base = Tb + fk * 25 + b;
+    double2 in[5], out[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) in[a] = base[5 * a];
+    dft5(in, w5, out);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) base[5 * c] = c == 0 ? out[0] : cmul(out[c], tw[16 * b * c]);   // 16 b c <= 256
+  }
+  __syncthreads();
+  // ---- stage B2: thread = (frame, k1, c): 5-point DFT over b of Z[b][c] -> bins k1 + 16 (c + 5 d), |X|^2
+  for (int item = tid; item < MEL_F * MEL_K1 * 5; item += MEL_THREADS) {
+    const int c = item % 5, fk = item / 5;
+    const int k1 = fk % MEL_K1, f = fk / MEL_K1;
+    const double2* base = Tb + fk * 25 + 5 * c;
+    double2 in[5], out[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) in[b] = base[b];
+    dft5(in, w5, out);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int k = k1 + 16 * (c + 5 * d);
+      const float p = (float)(out[d].x * out[d].x + out[d].y * out[d].y);
+      if (k >= 1 && k < MEL_BINS) pw[f * MEL_BINS + k] = p;
+      else if (k > 200 && k1 >= 1 && k1 <= 7) pw[f * MEL_BINS + 400 - k] = p;       // |X[400 - k]|^2 = |X[k]|^2 (real input)
     }
   }
   __syncthreads();
@@ -262,7 +272,7 @@ __global__ void mel_to_timemajor_kernel(const float* __restrict__ mel, int T, in
 
 // ------------------------------------------------------------------------------------------ host launchers
 size_t mel_power_smem_bytes() {
-  return sizeof(EO) * 2 * MEL_F * 100 + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
+  return sizeof(double2) * (400 + MEL_F * MEL_K1 * 25) + sizeof(float) * (MEL_SPAN + MEL_F * MEL_BINS);
 }
 
 cudaError_t launch_mel_power(const MelTables& tb, const void* pcm, bool pcm_i16, long long clip_stride, const int* n_valid_arr,

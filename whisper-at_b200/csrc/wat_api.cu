@@ -1152,8 +1152,8 @@ int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, floa
       fprintf(stderr, "sm %2d |", j);
       for (int k = 0; k < 7; ++k) fprintf(stderr, " %7lld", ht[j * 8 + k] ? ht[j * 8 + k] - t0 : -1);
       fprintf(stderr, " %s", ht[j * 8 + 7] ? "R" : " ");
-      fprintf(stderr, "   || mma: iter_start qk_issued p_seen v_seen pv_issued k_seen |");
-      for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", ht[512 + j * 8 + k] ? ht[512 + j * 8 + k] - t0 : -1);
+      fprintf(stderr, "   || mma: iter_start qk_issued p_seen v_seen pv_issued k_seen sfree_seen qk_mma_done |");
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", ht[512 + j * 8 + k] ? ht[512 + j * 8 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }
