@@ -65,6 +65,8 @@ def flops_per_clip(d: int, L: int, n_mels: int, low: bool, res: float):
 def hbm_bytes_per_clip(d: int, L: int, n_mels: int, bf16: bool):
     """Algorithmic bytes of the HBM-bound kernels per 30 s clip."""
     es = 2 if bf16 else 4
+    if bf16:      # no LayerNorm kernel in bf16 mode (folded into the GEMMs); every layer's pooling reads the bf16 copy of x
+        return dict(mel=480000 * 4 + 3000 * n_mels * es, pool=L * (1500 * d * 2 + 75 * d * 4))
     return dict(
         mel=480000 * 4 + 3000 * n_mels * es,                       # PCM fp32 in, time-major mel out
         layernorm=2 * L * 1500 * d * (4 + es) + (L - 1) * 75 * d * 4,   # 2 LN per layer: fp32 x in, xn out (+ fused pooled rows)
@@ -385,7 +387,7 @@ def main():
         # HBM-bound kernels: algorithmic bytes / measured device time (north_star: "achieved HBM GB/s for the mel and pooling kernels")
         hb = hbm_bytes_per_clip(d, L, n_mels, args.precision == "bf16")
         hbm = {}
-        for k in ("mel", "layernorm", "pool"):
+        for k in hb:
             t_ms = prof[k]["ms_per_step"]
             if t_ms > 0:
                 gbs = hb[k] * B / (t_ms / 1000.0) / 1e9

@@ -27,6 +27,15 @@ for r in rows[1:]:
     per.setdefault(lid, {})[m] = v
 
 
+# keep exactly ONE tagging call: from the first fill_kernel (the mel front end starts every call with it) up to the next one
+ids = sorted(per)
+starts = [i for i in ids if "fill_kernel" in names[i]]
+if len(starts) >= 2:
+    per = collections.OrderedDict((i, per[i]) for i in ids if starts[0] <= i < starts[1])
+elif len(starts) == 1:
+    per = collections.OrderedDict((i, per[i]) for i in ids if i >= starts[0])
+
+
 def klass(n):
     if "gemm_tc" in n: return "gemm"
     if "attn_tc" in n: return "attention"

@@ -38,7 +38,6 @@ namespace wat {
 // optional per-phase clock trace of one CTA (test hook wat_dbg_attention tc=3): slot = step * 8 + k
 #define AT_TRACE(base, step, k) do { if (TRACE && tr) tr[(base) + (step) * 8 + (k)] = clock64(); } while (0)
 
-constexpr int AT_THREADS = 160;                // 1 control warp (TMA + MMA issue) + 4 softmax warps
 constexpr int AT_KV = 64;                     // keys per step
 constexpr int AT_KSTAGE = 2;                  // K pipeline stages
 constexpr int AT_NSTAGE = 2;                  // V^T pipeline stages
@@ -161,26 +160,38 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
 // Pass 0: P = 2^S with no reference maximum (see the header).  POLY selects which pairs of every 8 scores take the FMA-pipe
 // polynomial instead of MUFU.EX2: bit p of POLY = pair p (scores 2p, 2p+1) of the group; the pattern alternates between the low
 // and the high nibble on odd groups so that e.g. 0x31 gives 1 of 4 and 2 of 4 pairs in turn (37.5%).
-template <bool MASK, bool TRACE, int POLY>
+template <bool MASK, bool TRACE, int POLY, int HALVES>
 __device__ __forceinline__ void softmax_tile_fast(uint32_t tS, uint32_t tP, int nvalid, int j, int n_kv, AttnBars* bars, float& l,
                                                   bool& s_next, long long* tr) {
-  uint32_t a[32], b[32];
-  tmem_ld32(tS, a);
-  tmem_ld32(tS + 32, b);
-  tc_wait_ld();
+  // HALVES = 2: two threads per query row (warps w and w + 4 share a TMEM lane quadrant), each takes 32 of the 64 keys of the
+  // step: tS / tP already point at this thread's columns and nvalid is relative to them.  Without a running maximum the two
+  // threads of a row never talk to each other until the row sums are added at the end of the tile.
+  constexpr int NC = 64 / HALVES;
+  uint32_t a[NC];
+  if constexpr (HALVES == 1) {
+    uint32_t lo[32], hi[32];
+    tmem_ld32(tS, lo);
+    tmem_ld32(tS + 32, hi);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { a[i] = lo[i]; a[32 + i] = hi[i]; }
+  } else {
+    tmem_ld32(tS, a);
+    tc_wait_ld();
+  }
   tc_fence_before();
   mbar_arrive(&bars->s_free);                                     // S is in registers: Q K(j+1)^T may overwrite the buffer
   AT_TRACE(0, j, 2);
   float2 ls0 = make_float2(0.f, 0.f), ls1 = ls0, ls2 = ls0, ls3 = ls0;
-  uint32_t pk[32];
+  uint32_t pk[NC / 2];
 #pragma unroll
-  for (int g4 = 0; g4 < 8; ++g4) {
+  for (int g4 = 0; g4 < NC / 8; ++g4) {
     float p[8];
     const int pat = (g4 & 1) ? (POLY >> 4) & 15 : POLY & 15;
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
       const int i = g4 * 8 + e;
-      const float2 x = make_float2(__uint_as_float(i < 32 ? a[i & 31] : b[i & 31]), __uint_as_float(i < 32 ? a[(i + 1) & 31] : b[(i + 1) & 31]));
+      const float2 x = make_float2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
       if ((pat >> (e >> 1)) & 1) {
         const float2 y = ex2_poly2_clamped(x);
         p[e] = y.x;
@@ -208,14 +219,15 @@ __device__ __forceinline__ void softmax_tile_fast(uint32_t tS, uint32_t tP, int 
     if (!okp) mbar_wait_spin(&bars->pv_done, (j - 1) & 1);
     tc_fence_after();
   }
-  tmem_st32(tP, pk);
+  if constexpr (HALVES == 1) tmem_st32(tP, pk);
+  else tmem_st16(tP, pk);
   tc_wait_st();
   const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
   l += t.x + t.y;
 }
 
-template <bool TRACE, int POLY>
-__global__ void __launch_bounds__(AT_THREADS, 3)
+template <bool TRACE, int POLY, int HALVES>
+__global__ void __launch_bounds__(32 + 128 * HALVES, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
                int q_tiles, float c_log2, int first_pass, int ctrl, long long* __restrict__ trace, unsigned int* __restrict__ n_repeat) {
@@ -233,8 +245,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = bh % n_head, b = bh / n_head;
   const int n_kv = (T + AT_KV - 1) / AT_KV;
 
-  // ctrl: which warp is the control warp (0 or 4); the other four are the softmax warps (TMEM lane quadrant = warp % 4)
-  const int first_sm = (ctrl + 1) % 5;
+  // the LAST warp is the control warp; warps 0 .. 4 HALVES - 1 are the softmax warps (TMEM lane quadrant = warp % 4, key half =
+  // warp / 4).  (ctrl is kept as a parameter for the launcher's sake; placing the control warp first made no difference.)
+  ctrl = 4 * HALVES;
+  const int first_sm = 0;
+  __shared__ float s_l[128 * HALVES];
   if (warp == ctrl && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -263,9 +278,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < AT_KSTAGE; ++s) mbar_init(&bars->k_full[s], 1);
     for (int s = 0; s < AT_NSTAGE; ++s) mbar_init(&bars->v_full[s], 1);
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->p_full, fast ? 128 * HALVES : 128);          // pass 1 (running max): one thread per row, warps 0..3
     mbar_init(&bars->pv_done, 1);
-    mbar_init(&bars->s_free, 128);
+    mbar_init(&bars->s_free, fast ? 128 * HALVES : 128);
     fence_mbar_init();
     // first loads right away: their latency (the Q tile is always a first touch) overlaps the TMEM allocation and the CTA
     // barrier below; nobody else touches these barriers before that barrier
@@ -368,8 +383,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       AT_TRACE(512, j, 4);
     }
-  } else {
+  } else if (fast || warp < 4) {
     const int q = warp & 3;
+    const int half = fast ? (warp >> 2) : 0;                      // which 32 keys of every step (two threads per row, pass 0)
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 24), row sum
@@ -383,8 +399,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off;
       if (fast) {
-        if (nvalid >= AT_KV) softmax_tile_fast<false, TRACE, POLY>(tS, tmem_P + lane_off, AT_KV, j, n_kv, bars, l, s_ready, tr);
-        else softmax_tile_fast<true, TRACE, POLY>(tS, tmem_P + lane_off, nvalid, j, n_kv, bars, l, s_ready, tr);
+        constexpr int NC = AT_KV / HALVES;
+        const uint32_t tSh = tS + half * NC, tPh = tmem_P + lane_off + half * (NC / 2);
+        if (nvalid >= AT_KV) softmax_tile_fast<false, TRACE, POLY, HALVES>(tSh, tPh, NC, j, n_kv, bars, l, s_ready, tr);
+        else softmax_tile_fast<true, TRACE, POLY, HALVES>(tSh, tPh, nvalid - half * NC, j, n_kv, bars, l, s_ready, tr);
       } else {
         if (nvalid >= AT_KV) softmax_tile<false, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, n_kv, bars, m_used, l, s_ready, tr);
         else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
@@ -396,33 +414,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_wait_spin(&bars->pv_done, (n_kv - 1) & 1);
     tc_fence_after();
+    // the row sum of a row whose keys were split over two threads
+    const int n_sm = fast ? 128 * HALVES : 128;                   // softmax threads of this pass
+    if (fast && HALVES == 2) {
+      s_l[half * 128 + r] = l;
+      named_bar_sync(1, n_sm);
+      l = s_l[r] + s_l[128 + r];
+    }
     // pass 0 is accepted iff every row sum stayed inside the exponent range (inf and NaN fail the comparisons too)
     if (fast && !(l >= 7.888609052e-31f && l <= 1.267650600e30f)) s_bad = 1;
-    named_bar_sync(1, 128);                                       // the four softmax warps
+    named_bar_sync(1, n_sm);
     if (!(fast && s_bad)) {
-    const int tq = qt * 128 + r;
-    __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64;
-    uint32_t v0[32], v1[32];
-    tmem_ld32(tmem_O + lane_off, v0);
-    tmem_ld32(tmem_O + lane_off + 32, v1);
-    tc_wait_ld();
-    const float inv = 1.0f / l;
-    if (tq < T) {
+      // O / l: with two threads per row each writes 32 of the head's 64 output columns
+      const int tq = qt * 128 + r;
+      const int ncol = (fast && HALVES == 2) ? 32 : 64, c0 = (fast && HALVES == 2) ? half * 32 : 0;
+      __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64 + c0;
+      const float inv = 1.0f / l;
+#pragma unroll 1
+      for (int cc = 0; cc < ncol; cc += 32) {
+        uint32_t v0[32];
+        tmem_ld32(tmem_O + lane_off + c0 + cc, v0);
+        tc_wait_ld();
+        if (tq < T) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        *reinterpret_cast<uint4*>(op + i) =
-            make_uint4(pack_bf16(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv),
-                       pack_bf16(__uint_as_float(v0[i + 2]) * inv, __uint_as_float(v0[i + 3]) * inv),
-                       pack_bf16(__uint_as_float(v0[i + 4]) * inv, __uint_as_float(v0[i + 5]) * inv),
-                       pack_bf16(__uint_as_float(v0[i + 6]) * inv, __uint_as_float(v0[i + 7]) * inv));
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        *reinterpret_cast<uint4*>(op + 32 + i) =
-            make_uint4(pack_bf16(__uint_as_float(v1[i]) * inv, __uint_as_float(v1[i + 1]) * inv),
-                       pack_bf16(__uint_as_float(v1[i + 2]) * inv, __uint_as_float(v1[i + 3]) * inv),
-                       pack_bf16(__uint_as_float(v1[i + 4]) * inv, __uint_as_float(v1[i + 5]) * inv),
-                       pack_bf16(__uint_as_float(v1[i + 6]) * inv, __uint_as_float(v1[i + 7]) * inv));
-    }
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(op + cc + i) =
+                make_uint4(pack_bf16(__uint_as_float(v0[i]) * inv, __uint_as_float(v0[i + 1]) * inv),
+                           pack_bf16(__uint_as_float(v0[i + 2]) * inv, __uint_as_float(v0[i + 3]) * inv),
+                           pack_bf16(__uint_as_float(v0[i + 4]) * inv, __uint_as_float(v0[i + 5]) * inv),
+                           pack_bf16(__uint_as_float(v0[i + 6]) * inv, __uint_as_float(v0[i + 7]) * inv));
+        }
+      }
     }
   }
   // end of the pass: the control warp joins the softmax warps; a rejected pass 0 is repeated as pass 1
@@ -449,16 +471,16 @@ static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuin
 }
 
 // POLY patterns of softmax_tile_fast (share of the exponentials evaluated on the FMA pipe): 0x11 = 25%, 0x31 = 37.5%, 0x33 = 50%
-template <int POLY>
+template <int POLY, int HALVES>
 static cudaError_t launch_attn_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, __nv_bfloat16* out, int grid,
                                        int T, int D, int n_head, int q_tiles, float c_log2, int first_pass, long long* trace,
                                        unsigned int* n_repeat, cudaStream_t st) {
   static unsigned long long attr_mask = 0, attr_mask_tr = 0;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false, POLY>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true, POLY>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
-  static const int ctrl = getenv("WAT_ATTN_CTRL") ? atoi(getenv("WAT_ATTN_CTRL")) : 4;
-  if (trace) attn_tc_kernel<true, POLY><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, ctrl ? 4 : 0, trace, n_repeat);
-  else attn_tc_kernel<false, POLY><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, ctrl ? 4 : 0, nullptr, n_repeat);
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false, POLY, HALVES>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true, POLY, HALVES>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
+  constexpr int threads = 32 + 128 * HALVES;
+  if (trace) attn_tc_kernel<true, POLY, HALVES><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, 0, trace, n_repeat);
+  else attn_tc_kernel<false, POLY, HALVES><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, 0, nullptr, n_repeat);
   return cudaGetLastError();
 }
 
@@ -488,10 +510,14 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   static const int fast_on = getenv("WAT_ATTN_FAST") ? atoi(getenv("WAT_ATTN_FAST")) : 1;
   static const int poly = getenv("WAT_ATTN_POLY") ? atoi(getenv("WAT_ATTN_POLY")) : 1;
   const int first_pass = (fast_on && q_prescaled) ? 0 : 1;
-  if (poly == 0) return launch_attn_variant<0x11>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
-  if (poly == 2) return launch_attn_variant<0x33>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
-  if (poly == 3) return launch_attn_variant<0x00>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
-  return launch_attn_variant<0x31>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st);
+  // HALVES = 2 (two threads per query row in the max-free pass, 9 warps per CTA) is implemented above and was measured:
+  // 94 ms per step against 81 ms for one thread per row on the same box - more warps per step cost more in hand-overs and
+  // registers (72 per thread) than the shorter per-thread exponential phase gains.  Only HALVES = 1 is instantiated.
+#define WAT_ATTN_LAUNCH(P, H) launch_attn_variant<P, H>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st)
+  if (poly == 0) return WAT_ATTN_LAUNCH(0x11, 1);
+  if (poly == 2) return WAT_ATTN_LAUNCH(0x33, 1);
+  return WAT_ATTN_LAUNCH(0x31, 1);
+#undef WAT_ATTN_LAUNCH
 }
 
 }  // namespace wat
