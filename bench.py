@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0, help="clips per internal chunk of the library (0 = the whole per-GPU batch)")
     ap.add_argument("--profile-steps", type=int, default=2, help="extra steps run with per-launch CUDA events for the kernel-class breakdown")
+    ap.add_argument("--long-file-minutes", type=float, default=30.0,
+                    help="N=1 only: also time model.transcribe() on one synthetic file of this length (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true", help="profiling runs only: do not force W >= 3")
@@ -424,6 +426,22 @@ def main():
         per_kind = {"gemm_qkv": 2 * T * 3 * d * d, "gemm_out": 2 * T * d * d, "gemm_fc1": 2 * T * 4 * d * d, "gemm_fc2": 2 * T * 4 * d * d}
         out["roofline"]["encoder_gemm_tflops"] = {k: (f * L * B / (prof[k]["ms_per_step"] / 1000.0) / 1e12) if prof[k]["ms_per_step"] > 0 else None
                                                   for k, f in per_kind.items()}
+        if world == 1 and args.long_file_minutes > 0:
+            # the reference-facing API on a long file: log-mel of the whole file, all 30 s windows through the encoder in batches,
+            # the head batched per at_start, rows placed as transcribe.py:255-263 does (fixed 30 s stride)
+            import warnings
+            n_win = max(1, int(args.long_file_minutes * 2))
+            long_audio = torch.cat([base[i % base.shape[0]] for i in range(n_win)])
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model.transcribe(long_audio[:480000 * min(n_win, 2)], at_time_res=res)          # warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = model.transcribe(long_audio, at_time_res=res)
+                dt = time.perf_counter() - t0
+            out["long_file"] = dict(api="Whisper.transcribe(audio, at_time_res)", minutes=n_win / 2, windows=n_win,
+                                    audio_tag_rows=int(r["audio_tag"].shape[0]), seconds=dt, value=30.0 * n_win / dt, unit=UNIT,
+                                    note="host waveform in, CPU audio_tag out; includes the H2D of the waveform and the whole-file log-mel")
         if world == 1 and not args.no_gpu_baseline and args.precision == "bf16":
             te_ = time_torch_eager(sd, h, n_mels, audio_dev, audio_host, res, max(2, min(args.steps, 5)), 2, ours_logits=lg)
             s_ = te_["sdpa"]

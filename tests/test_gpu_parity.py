@@ -368,6 +368,43 @@ def test_asr_handoff_x_out_feeds_the_text_decoder(golden_dir, precision, tol):
             assert max_abs(all_x[:, ::5, ::3], ref_p) <= (1e-3 if precision == "fp32" else TOL_POOLED_BF16) * max(1.0, float(ref_p.abs().max()))
 
 
+def test_transcribe_hands_the_encoder_output_to_a_text_decoder(golden_dir):
+    """transcribe(asr_decoder=fn): ONE encoder pass per window batch yields the tagging states and ln_post(x); fn receives the
+    latter for every window and its texts come back in the result, next to audio_tag rows that are unchanged."""
+    z = golden(golden_dir, "decoder_tiny")
+    d, h, L = synth.MODEL_SHAPES["tiny"]
+    m, sd, _ = model_for("tiny", seed=1, init="lively", precision="fp32")
+    dsd = {k: v.cuda() for k, v in synth.synth_decoder_state_dict(d, 2, 1024, 64, seed=1).items()}
+    tokens = torch.from_numpy(z["tokens"]).cuda()[:1]
+    calls = []
+
+    def greedy_first_token(audio_features, seeks):
+        calls.append((tuple(audio_features.shape), list(seeks)))
+        lg = O.text_decoder_logits(tokens.expand(audio_features.shape[0], -1), audio_features, dsd, h)
+        return [{"text": f"<{int(t)}>"} for t in lg[:, -1].argmax(-1)]
+
+    audio = torch.cat([synth.synth_clip(1), synth.synth_clip(2)])                   # 60 s -> two windows
+    launches0 = m.kernel_launches()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = m.transcribe(audio, at_time_res=10, fp16=False, asr_decoder=greedy_first_token)
+        launches_with = m.kernel_launches() - launches0
+        r0 = m.transcribe(audio, at_time_res=10, fp16=False)
+    assert calls == [((2, 1500, d), [0, 3000])]                                     # one call, both windows, one encoder batch
+    # expected next tokens: the oracle's encoder + the same decoder on the file's two windows (the file-level log-mel clamp makes
+    # them differ slightly from the per-clip fixtures)
+    mel = O.log_mel(audio, 80, padding=480000)
+    dsd_cpu = {k: v.cpu() for k, v in dsd.items()}
+    ref_tok = []
+    for seek in (0, 3000):
+        _, x_o = O.encoder_pooled(mel[None, :, seek:seek + 3000], sd, h, return_x=True)
+        ref_tok.append(int(O.text_decoder_logits(tokens.cpu(), x_o, dsd_cpu, h)[0, -1].argmax()))
+    assert r["text"] == "".join(f"<{t}>" for t in ref_tok)
+    assert [s["seek"] for s in r["segments"]] == [0, 3000] and r["segments"][1]["start"] == 30.0
+    assert torch.equal(r["audio_tag"], r0["audio_tag"]) and r0["text"] == "" and r0["segments"] == []
+    assert launches_with <= (m.kernel_launches() - launches0 - launches_with) + 2    # the hand-off costs one ln_post launch, not an encoder pass
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_two_devices_in_one_process():
     """a handle per device in ONE process (not torchrun): the shared-memory opt-ins are per device, every entry point

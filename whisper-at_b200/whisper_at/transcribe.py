@@ -1,10 +1,18 @@
 """`transcribe()` for the tagging path: same signature, `at_time_res` checks, window arithmetic and result
 dict as the reference (package/whisper-at/whisper_at/transcribe.py:38-403), without the ASR decoder.
 
-What differs: no text is produced (`text` == "", `segments` == []), and multi-window files advance by a
-fixed 30 s stride; the reference advances `seek` by what its ASR decoder's timestamp tokens say
-(transcribe.py:276-343), which is outside this path.  For audio of up to 30 s (one window, seek == 0) the
-`audio_tag` rows are the reference's.  All windows of a file go through the encoder as ONE batch.
+What differs: this package has no text decoder of its own (`text` == "", `segments` == [] unless the caller
+supplies one, see `asr_decoder`), and multi-window files advance by a fixed 30 s stride; the reference advances
+`seek` by what its ASR decoder's timestamp tokens say (transcribe.py:276-343), which is outside this path.  For
+audio of up to 30 s (one window, seek == 0) the `audio_tag` rows are the reference's.  All windows of a file go
+through the encoder as ONE batch.
+
+ASR hand-off: the same encoder pass that yields the pooled tagging states also yields
+`ln_post(x)` - what the reference's `TextDecoder` cross-attends to (model.py:175, 200-222).  Pass
+`asr_decoder=fn` and `fn(audio_features, seeks)` is called once per encoder batch with `audio_features`
+[n_windows, 1500, d] fp32 on the model's device and the windows' start frames; it returns one dict per window
+(`{"text": str, ...}`), which become `segments`, their texts joined into `text`.  The reference instead re-runs
+the encoder inside every `model.decode` call of its temperature fall-back loop (transcribe.py:160-198).
 """
 from __future__ import annotations
 
@@ -45,6 +53,7 @@ def transcribe(
     prepend_punctuations: str = "\"'“¿([{-",
     append_punctuations: str = "\"'.。,，!！?？:：”)]}、",
     at_time_res=10,
+    asr_decoder=None,
     **decode_options,
 ):
     """Tag an audio file / waveform.  Returns {"text", "segments", "language", "at_time_res", "audio_tag"} with
@@ -63,13 +72,24 @@ def transcribe(
     n_rows = math.ceil(content_frames / at_decision_window)
     all_audio_tags = torch.zeros([n_rows, 527])
     seeks = list(range(0, content_frames, N_FRAMES))
+    segments = []
     if seeks:
         segs = torch.stack([pad_or_trim(mel[:, s:s + N_FRAMES], N_FRAMES) for s in seeks])       # transcribe.py:241-244
         chunk = max(1, model.max_batch)
         for c0 in range(0, len(seeks), chunk):
-            all_x = model._encode(segs[c0:c0 + chunk], precision=precision)
+            if asr_decoder is not None:                          # one encoder pass serves tagging AND the caller's text decoder
+                x_post, all_x = model._encode(segs[c0:c0 + chunk], want_x=True, precision=precision)
+            else:
+                all_x = model._encode(segs[c0:c0 + chunk], precision=precision)
             if all_x.ndim == 3:
                 all_x = all_x[None]
+            if asr_decoder is not None:
+                for seek, seg in zip(seeks[c0:c0 + chunk], asr_decoder(x_post, seeks[c0:c0 + chunk])):
+                    seg = dict(seg)
+                    seg.setdefault("seek", seek)
+                    seg.setdefault("start", seek * HOP_LENGTH / SAMPLE_RATE)
+                    seg.setdefault("end", min(content_frames, seek + N_FRAMES) * HOP_LENGTH / SAMPLE_RATE)
+                    segments.append(seg)
             # windows that share an at_start go through the head as ONE batch (wat_tltr takes [n, L, 75 - at_start, d]);
             # there are at most window / gcd(window, 3000) distinct values
             groups = {}
@@ -86,4 +106,5 @@ def transcribe(
                 cur_start = math.floor(seek / at_decision_window)
                 cur_end = min(all_audio_tags.shape[0], cur_start + audio_tag.shape[0])
                 all_audio_tags[cur_start:cur_end, :] = audio_tag[0:cur_end - cur_start, :]       # transcribe.py:261-263
-    return dict(text="", segments=[], language=language, at_time_res=at_time_res, audio_tag=all_audio_tags.cpu())
+    text = "".join(str(seg.get("text", "")) for seg in segments)
+    return dict(text=text, segments=segments, language=language, at_time_res=at_time_res, audio_tag=all_audio_tags.cpu())
