@@ -510,6 +510,9 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   static const int fast_on = getenv("WAT_ATTN_FAST") ? atoi(getenv("WAT_ATTN_FAST")) : 1;
   static const int poly = getenv("WAT_ATTN_POLY") ? atoi(getenv("WAT_ATTN_POLY")) : 1;
   const int first_pass = (fast_on && q_prescaled) ? 0 : 1;
+  // Measured without gain on top of this kernel (round 2): loading S from TMEM in two halves with the second load in flight
+  // during the first half's exponentials, and asking for PV(j-1)'s completion at the start of the step (79.6-81.8 ms vs 81.0
+  // on the same box) - the per-step latencies are hidden by the three co-resident CTAs, not exposed.
   // HALVES = 2 (two threads per query row in the max-free pass, 9 warps per CTA) is implemented above and was measured:
   // 94 ms per step against 81 ms for one thread per row on the same box - more warps per step cost more in hand-overs and
   // registers (72 per thread) than the shorter per-thread exponential phase gains.  Only HALVES = 1 is instantiated.
