@@ -424,6 +424,11 @@ def main():
             out["gather_check"] = gather_check
         T = 1500
         per_kind = {"gemm_qkv": 2 * T * 3 * d * d, "gemm_out": 2 * T * d * d, "gemm_fc1": 2 * T * 4 * d * d, "gemm_fc2": 2 * T * 4 * d * d}
+        head_ms = sum(prof[k]["ms_per_step"] for k in ("gemm_head", "head_attention", "mean") if k in prof)
+        out["roofline"]["head"] = dict(ms_per_step=head_ms, note="TL-TR head: its GEMMs (incl. classifier), short-sequence attention and group means; "
+                                       "window regroup and the head's LayerNorms are in 'layout' / 'layernorm'",
+                                       gemm_tflops=((fl["gemm"] - (fl["encoder"] - L * 4 * 1500 * 1500 * d)) * B / (prof["gemm_head"]["ms_per_step"] / 1000.0) / 1e12)
+                                       if prof.get("gemm_head", {}).get("ms_per_step", 0) > 0 else None)
         out["roofline"]["encoder_gemm_tflops"] = {k: (f * L * B / (prof[k]["ms_per_step"] / 1000.0) / 1e12) if prof[k]["ms_per_step"] > 0 else None
                                                   for k, f in per_kind.items()}
         if world == 1 and args.long_file_minutes > 0:

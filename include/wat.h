@@ -166,12 +166,13 @@ WAT_API int wat_dbg_gemm(const float* A, const float* W, const float* bias, cons
 WAT_API int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, void* vt, int32_t M, int32_t N, int32_t K,
                       int32_t act, int32_t seq_T, int32_t seq_Tpad, int32_t n_head, void* stream);
 /* a LayerNorm folded into the GEMM that consumes it, chained as the bf16 encoder does (see DESIGN.md "LayerNorm folding"):
- * x = R + A1 W1^T + bias1 (fp32; the epilogue also leaves xb = bf16(x), per-slice row statistics and 20-row pooled means),
+ * x = R + A1 W1^T + bias1 (R / x fp32, or fp16 when x_f16 - the bf16 encoder's residual stream; the epilogue also leaves
+ * xb = bf16(x), per-slice row statistics; pooled = 20-row means of xb),
  * then out = act(LN(x; gamma, beta) W2^T + bias2) as rstd (xb W2'^T - mean colsum) + bias2'.  All pointers device. */
 WAT_API int wat_dbg_ln_slices(int32_t M, int32_t D, int32_t K1, int32_t pair);
-WAT_API int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const float* R, float* x, void* xb, float* stats,
+WAT_API int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const void* R, void* x, void* xb, float* stats,
                     float* pooled, const float* W2, const float* gamma, const float* beta, const float* bias2, void* out, int32_t M,
-                    int32_t D, int32_t K1, int32_t N2, int32_t act, int32_t pair, void* stream);
+                    int32_t D, int32_t K1, int32_t N2, int32_t act, int32_t pair, int32_t x_f16, void* stream);
 /* x [B*T, D] fp32, wqkv [3D, D], bqkv [3D] -> out [B*T, D]: fused-QKV GEMM + encoder self-attention (hd 64) */
 WAT_API int wat_dbg_attention(const float* x, const float* wqkv, const float* bqkv, float* out, int32_t B, int32_t T,
                       int32_t n_head, int32_t tc, void* stream);

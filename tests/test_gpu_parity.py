@@ -215,7 +215,8 @@ def test_bf16_epilogues_at_encoder_shapes(M, N, K, kind):
 
 @pytest.mark.parametrize("M,D,K1,N2,act,pair", [(3000, 1280, 1280, 5120, 1, 1), (3000, 1280, 5120, 3840, 0, 1), (1500, 384, 384, 1536, 1, -1),
                                                 (1500, 768, 768, 768, 0, -1), (777, 512, 2048, 1024, 0, 1), (100, 512, 512, 512, 1, 0)])
-def test_layernorm_folded_into_gemm(M, D, K1, N2, act, pair):
+@pytest.mark.parametrize("x_f16", [0, 1], ids=["x_fp32", "x_fp16"])
+def test_layernorm_folded_into_gemm(M, D, K1, N2, act, pair, x_f16):
     """the bf16 encoder has no LayerNorm kernel: the producing GEMM's epilogue leaves bf16(x), per-slice row statistics and the
     20x pooled means; the consuming GEMM computes LN(x) W^T + b as rstd (x W'^T - mean colsum) + b'.  Both halves against torch."""
     g = torch.Generator(device="cpu").manual_seed(M + D + K1)
@@ -229,18 +230,27 @@ def test_layernorm_folded_into_gemm(M, D, K1, N2, act, pair):
     b2 = torch.randn(N2, generator=g).cuda()
     L = _lib.lib()
     np_ = L.wat_dbg_ln_slices(M, D, K1, pair)
-    x = torch.empty(M, D, device="cuda")
+    if x_f16:                                                    # the bf16 encoder keeps the residual stream in fp16 (the reference's GPU dtype)
+        R = R.half()
+    x = torch.empty(M, D, device="cuda", dtype=torch.float16 if x_f16 else torch.float32)
     xb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
     stats = torch.full((M, np_, 2), float("nan"), device="cuda")
     pooled = torch.full((M // 1500, 1, 75, D), float("nan"), device="cuda") if M % 1500 == 0 else None
     out = torch.empty(M, N2, device="cuda", dtype=torch.bfloat16)
     _lib.check(L.wat_dbg_ln_gemm(A1.data_ptr(), W1.data_ptr(), b1.data_ptr(), R.data_ptr(), x.data_ptr(), xb.data_ptr(), stats.data_ptr(),
                                  pooled.data_ptr() if pooled is not None else None, W2.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                 b2.data_ptr(), out.data_ptr(), M, D, K1, N2, act, pair, torch.cuda.current_stream().cuda_stream))
+                                 b2.data_ptr(), out.data_ptr(), M, D, K1, N2, act, pair, x_f16, torch.cuda.current_stream().cuda_stream))
     x_ref = R.double() + A1.double() @ W1.double().T + b1.double()
-    assert max_abs(x, x_ref) <= 2e-4 * max(1.0, float(x_ref.abs().max()))
-    assert torch.equal(xb, x.bfloat16())                                                 # the copy is the rounded fp32 row
-    assert max_abs(stats[..., 0].sum(1), x.double().sum(1)) <= 1e-3 and max_abs(stats[..., 1].sum(1), (x.double() ** 2).sum(1)) <= 2e-2
+    xmax = max(1.0, float(x_ref.abs().max()))
+    if x_f16:
+        assert max_abs(x, x_ref) <= 2 ** -10 * xmax                                      # one fp16 rounding of the fp32 row
+        assert max_abs(xb, x_ref) <= 2 ** -7 * xmax                                      # bf16 copy of the SAME fp32 row (not of fp16(x))
+        assert max_abs(stats[..., 0].sum(1), x_ref.sum(1)) <= 1e-3 * xmax and max_abs(stats[..., 1].sum(1), (x_ref ** 2).sum(1)) <= 2e-2 * xmax
+        x = x.float()
+    else:
+        assert max_abs(x, x_ref) <= 2e-4 * xmax
+        assert torch.equal(xb, x.bfloat16())                                             # the copy is the rounded fp32 row
+        assert max_abs(stats[..., 0].sum(1), x.double().sum(1)) <= 1e-3 and max_abs(stats[..., 1].sum(1), (x.double() ** 2).sum(1)) <= 2e-2
     if pooled is not None:
         assert max_abs(pooled[:, 0], xb.double().reshape(-1, 75, 20, D).mean(2)) <= 1e-6 * max(1.0, float(x_ref.abs().max()))
         assert max_abs(pooled[:, 0], x.double().reshape(-1, 75, 20, D).mean(2)) <= 2e-3 * max(1.0, float(x_ref.abs().max()))

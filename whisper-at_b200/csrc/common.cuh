@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -409,6 +410,18 @@ __device__ __forceinline__ void gelu_erf_poly8(float* v) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// fp16 storage of the residual stream (bf16 mode): 4 values <-> 8 bytes; conversion to fp16 saturates instead of producing inf
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float4 f16x4_to_f32(uint32_t a, uint32_t b) {
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -43,6 +43,7 @@ struct GemmTcDev {
   int tma_store;           // bf16 outputs leave through smem + TMA store (CTA-pair kernel)
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
   float q_scale;           // QKV epilogue: q columns [0, D) are multiplied by it (0 = off)
+  int c_f16, r_f16;        // fp32 epilogues: C is stored / R is read as fp16 (the bf16 mode's residual stream)
   // fp32 epilogues as PRODUCER of the next LayerNorm (see kernels.h GemmTc): bf16 copy, per-slice row statistics
   __nv_bfloat16* xb; long long ldxb;
   float* stats; int stats_np;
@@ -64,7 +65,12 @@ __device__ __forceinline__ void load_residual_chunk(const GemmTcDev& g, int row_
     res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grow < g.M && n0 < g.N) {
       const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
-      res[it] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+      if (g.r_f16) {                                              // 4 halves: the raw bits travel in .x / .y and are converted at use
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(g.R) + rrow * g.ldr + n0 + cc);
+        res[it].x = __uint_as_float(u.x); res[it].y = __uint_as_float(u.y);
+      } else {
+        res[it] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+      }
     }
   }
 }
@@ -111,7 +117,12 @@ __device__ __forceinline__ void load_residual_rows(const GemmTcDev& g, int row_b
     res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grow < g.M && n0 < g.N) {
       const long long rrow = g.r_mod > 0 ? (grow % g.r_mod) : grow;
-      res[k] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+      if (g.r_f16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(g.R) + rrow * g.ldr + n0 + cc);
+        res[k].x = __uint_as_float(u.x); res[k].y = __uint_as_float(u.y);
+      } else {
+        res[k] = *reinterpret_cast<const float4*>(g.R + rrow * g.ldr + n0 + cc);
+      }
     }
   }
 }
@@ -120,20 +131,29 @@ __device__ __forceinline__ void load_residual_rows(const GemmTcDev& g, int row_b
 // chunk's stores are issued (the residual stream is updated in place, but a chunk's own columns are only read before they are
 // written).
 template <int NIT>
-__device__ __forceinline__ void epi_rows(const GemmTcDev& g, const float* stage, float2* rowacc, int row_base, int n0, int lane, int it0,
+__device__ __forceinline__ void epi_rows_generic(const GemmTcDev& g, const float* stage, float2* rowacc, int row_base, int n0, int lane, int it0,
                                          float4 (&res)[NIT], bool add_res, int nxt_row_base = -1, int nxt_n0 = 0) {
   const int cc = (lane & 7) * 4;
   float4 t[NIT];
 #pragma unroll
   for (int k = 0; k < NIT; ++k) {
     t[k] = *reinterpret_cast<const float4*>(stage + ((it0 + k) * 4 + (lane >> 3)) * 36 + cc);
-    if (add_res) { t[k].x += res[k].x; t[k].y += res[k].y; t[k].z += res[k].z; t[k].w += res[k].w; }
+    if (add_res) {
+      const float4 rv = g.r_f16 ? f16x4_to_f32(__float_as_uint(res[k].x), __float_as_uint(res[k].y)) : res[k];
+      t[k].x += rv.x; t[k].y += rv.y; t[k].z += rv.z; t[k].w += rv.w;
+    }
   }
   if (nxt_row_base >= 0) load_residual_rows<NIT>(g, nxt_row_base, nxt_n0, lane, 0, res);
 #pragma unroll
   for (int k = 0; k < NIT; ++k) {
     const int grow = row_base + (it0 + k) * 4 + (lane >> 3);
-    if (grow < g.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t[k];
+    if (grow < g.M) {
+      if (g.c_f16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.C) + (long long)grow * g.ldc + n0 + cc) =
+            make_uint2(pack_f16_sat(t[k].x, t[k].y), pack_f16_sat(t[k].z, t[k].w));
+      else
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + (long long)grow * g.ldc + n0 + cc) = t[k];
+    }
   }
   // ---- this output feeds a LayerNorm: what the (folded) consumer needs is produced here, while the values are in registers
   if (g.xb) {                                                     // bf16 copy of the rows: the next GEMM's A operand
@@ -156,6 +176,75 @@ __device__ __forceinline__ void epi_rows(const GemmTcDev& g, const float* stage,
       acc.y = fmaf(t[k].x, t[k].x, fmaf(t[k].y, t[k].y, fmaf(t[k].z, t[k].z, fmaf(t[k].w, t[k].w, acc.y))));
       *a = acc;
     }
+  }
+}
+// The same for the case the bf16 encoder runs ~all the time - C in fp16 with its bf16 copy and the row statistics, every row of
+// the chunk inside the matrix: no per-row bounds checks, one base pointer per stream advanced by a constant stride (the generic
+// version above spends ~600 of its ~900 instructions per chunk on 64-bit address arithmetic, predicates and flag tests).
+template <int NIT, bool RF16>
+__device__ __forceinline__ void load_residual_rows_fast(const GemmTcDev& g, int row_base, int n0, int lane, int it0, float4 (&res)[NIT]) {
+  const long long e0 = (long long)(row_base + it0 * 4 + (lane >> 3)) * g.ldr + n0 + (lane & 7) * 4;
+  const long long step = 4 * g.ldr;
+  if (RF16) {
+    const __half* rp = reinterpret_cast<const __half*>(g.R) + e0;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const uint2 u = *reinterpret_cast<const uint2*>(rp + k * step);
+      res[k].x = __uint_as_float(u.x); res[k].y = __uint_as_float(u.y);
+    }
+  } else {
+    const float* rp = g.R + e0;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) res[k] = *reinterpret_cast<const float4*>(rp + k * step);
+  }
+}
+template <int NIT, bool RF16>
+__device__ __forceinline__ void epi_rows_fast(const GemmTcDev& g, const float* stage, float2* rowacc, int row_base, int n0, int lane, int it0,
+                                              float4 (&res)[NIT], bool add_res, int nxt_row_base, int nxt_n0) {
+  const int cc = (lane & 7) * 4, lrow = it0 * 4 + (lane >> 3);
+  float4 t[NIT];
+  const float* sp = stage + lrow * 36 + cc;
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    t[k] = *reinterpret_cast<const float4*>(sp + k * 4 * 36);
+    if (add_res) {
+      const float4 rv = RF16 ? f16x4_to_f32(__float_as_uint(res[k].x), __float_as_uint(res[k].y)) : res[k];
+      t[k].x += rv.x; t[k].y += rv.y; t[k].z += rv.z; t[k].w += rv.w;
+    }
+  }
+  if (nxt_row_base >= 0) {
+    if (g.r_mod == 0 && nxt_row_base + 32 <= g.M && nxt_n0 < g.N) load_residual_rows_fast<NIT, RF16>(g, nxt_row_base, nxt_n0, lane, 0, res);
+    else load_residual_rows<NIT>(g, nxt_row_base, nxt_n0, lane, 0, res);
+  }
+  {
+    __half* cp = reinterpret_cast<__half*>(g.C) + (long long)(row_base + lrow) * g.ldc + n0 + cc;
+    const long long step = 4 * g.ldc;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) *reinterpret_cast<uint2*>(cp + k * step) = make_uint2(pack_f16_sat(t[k].x, t[k].y), pack_f16_sat(t[k].z, t[k].w));
+  }
+  {
+    __nv_bfloat16* xp = g.xb + (long long)(row_base + lrow) * g.ldxb + n0 + cc;
+    const long long step = 4 * g.ldxb;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) *reinterpret_cast<uint2*>(xp + k * step) = make_uint2(pack_bf16(t[k].x, t[k].y), pack_bf16(t[k].z, t[k].w));
+  }
+  float2* a = rowacc + it0 * 32 + lane;
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    float2 acc = a[k * 32];
+    acc.x += (t[k].x + t[k].y) + (t[k].z + t[k].w);
+    acc.y = fmaf(t[k].x, t[k].x, fmaf(t[k].y, t[k].y, fmaf(t[k].z, t[k].z, fmaf(t[k].w, t[k].w, acc.y))));
+    a[k * 32] = acc;
+  }
+}
+template <int NIT>
+__device__ __forceinline__ void epi_rows(const GemmTcDev& g, const float* stage, float2* rowacc, int row_base, int n0, int lane, int it0,
+                                         float4 (&res)[NIT], bool add_res, int nxt_row_base = -1, int nxt_n0 = 0) {
+  if (g.c_f16 && g.xb && rowacc && row_base + 32 <= g.M && (!add_res || g.r_mod == 0)) {           // warp-uniform
+    if (g.r_f16) epi_rows_fast<NIT, true>(g, stage, rowacc, row_base, n0, lane, it0, res, add_res, nxt_row_base, nxt_n0);
+    else epi_rows_fast<NIT, false>(g, stage, rowacc, row_base, n0, lane, it0, res, add_res, nxt_row_base, nxt_n0);
+  } else {
+    epi_rows_generic<NIT>(g, stage, rowacc, row_base, n0, lane, it0, res, add_res, nxt_row_base, nxt_n0);
   }
 }
 // `res` (optional): the residual block of THIS chunk, loaded by the caller ahead of time; it is refilled with the block at
@@ -738,7 +827,7 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi; d.tma_store = 0;
-  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale; d.c_f16 = g.c_f16; d.r_f16 = g.r_f16;
   d.trace = nullptr;
   d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
   d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;
@@ -761,7 +850,7 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
   d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi;
-  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale;
+  d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale; d.c_f16 = g.c_f16; d.r_f16 = g.r_f16;
   d.trace = g.trace;
   d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
   d.ln_stats = g.ln_stats; d.ln_np = g.ln_np; d.ln_colsum = g.ln_colsum;

@@ -70,8 +70,10 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
 
 // mean over groups of `win` consecutive rows: x [n_groups*win, D] (row stride D) -> out row g at out + g*out_stride
 // optional xb [n_groups, D] bf16 + stats [n_groups, 1, 2]: the row's bf16 copy and (sum, sum of squares) for a folded LayerNorm
-cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride,
+// x / out rows are fp32 or fp16 (in_f16 / out_f16; fp16 = the bf16 mode's residual stream)
+cudaError_t launch_group_mean(const void* x, bool in_f16, int n_groups, int win, int D, void* out, bool out_f16, long long out_stride,
                               cudaStream_t st, __nv_bfloat16* xb = nullptr, float* stats = nullptr);
+cudaError_t launch_layernorm_f16in(const void* x, const float* gamma, const float* beta, int M, int D, float* out, cudaStream_t st);
 // encoder pooling: x [B, 1500, D] -> pooled[b, layer, 0..74, :] with pooled laid out [B, L, 75, D]
 cudaError_t launch_pool20(const float* x, int B, int T, int D, int layer, int L, float* pooled, cudaStream_t st);
 // the same from the bf16 copy of the residual stream the fc2 epilogue leaves (bf16 mode): half the bytes; rows summed in fp32
@@ -88,10 +90,10 @@ cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n
 // TL-TR window regroup (model.py:360-367): pooled [B, L, Tp, D] -> rows (b, s, l, tau), zero rows past Tp
 // baseline heads: reduce the layer axis first (kind 0 = mean, 1 = last layer, 2 = weights w[L] / sum(w)); out rows = (b*S + s)*dw + tau
 cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                                     int kind, const float* w, float* out, cudaStream_t st, __nv_bfloat16* xb = nullptr,
+                                     int kind, const float* w, void* out, bool out_f16, cudaStream_t st, __nv_bfloat16* xb = nullptr,
                                      float* stats = nullptr);
 cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S,
-                               int D, float* out, cudaStream_t st, __nv_bfloat16* xb = nullptr, float* stats = nullptr);
+                               int D, void* out, bool out_f16, cudaStream_t st, __nv_bfloat16* xb = nullptr, float* stats = nullptr);
 // W' = bf16(W diag(gamma)) [N, K], colsum [N], bias_out [N] = bias + W beta  (LayerNorm folded into the GEMM that consumes it)
 cudaError_t launch_fold_ln_weights(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
                                    __nv_bfloat16* Wout, float* colsum, float* bias_out, cudaStream_t st);
@@ -124,6 +126,9 @@ struct GemmTc {
   // CONSUMER side: A holds un-normalised rows; out = rstd (A W'^T - mean colsum) + bias with the rows' mean / rstd from
   // ln_stats [M, ln_np, 2] and W', colsum, bias prepared by launch_fold_ln_weights
   const float* ln_stats; int ln_np; const float* ln_colsum;
+  // fp32 epilogues: C is stored / R is read as fp16 with the same leading dimensions in elements (bf16 mode keeps the residual
+  // stream in fp16, the dtype the reference's own GPU path uses for it; the arithmetic stays fp32)
+  int c_f16, r_f16;
 };
 cudaError_t launch_gemm_tc(const GemmTc& g, int num_sms, cudaStream_t st);
 int gemm_tc_stats_slices(int M, int N, int K, int epi, int force_pair);

@@ -70,6 +70,17 @@ cudaError_t launch_gemm_f32(const GemmF32& g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
+// rows of the residual stream are fp32 (fp32 mode) or fp16 (bf16 mode): 4 elements at a time
+__device__ __forceinline__ float4 ldrow4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldrow4(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return f16x4_to_f32(u.x, u.y);
+}
+__device__ __forceinline__ void strow4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void strow4(__half* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16_sat(v.x, v.y), pack_f16_sat(v.z, v.w));
+}
+
 template <typename OutT>
 __device__ __forceinline__ void store4(OutT* p, float4 v);
 template <>
@@ -116,8 +127,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // same, with the row held in registers (one global read; D a multiple of 128, <= 1280): every load of a row is in
 // flight before the first reduction starts
-template <typename OutT>
-__global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <typename OutT, typename InT = float>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const InT* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int M, int D, OutT* __restrict__ out) {
   // rows are walked from the END: the producer GEMM wrote the residual stream front to back, so its last row blocks are
   // the ones still in L2; and the rows normalised last (the first ones) are what the next GEMM reads first
@@ -125,13 +136,13 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restr
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int n4 = D >> 7;
-  const float* xr = x + (long long)row * D;
+  const InT* xr = x + (long long)row * D;
   float4 v[10];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 10; ++i)
     if (i < n4) {
-      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+      v[i] = ldrow4(xr + (i * 32 + lane) * 4);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   const float inv_d = 1.0f / (float)D;
@@ -158,6 +169,14 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* __restr
       y.w = (v[i].w - mean) * rstd * gm.w + bt.w;
       store4<OutT>(o + c, y);
     }
+}
+
+// x rows in fp16 (the bf16 mode's residual stream) -> fp32 LayerNorm output (ln_post for the ASR hand-off); D % 128 == 0, <= 1280
+cudaError_t launch_layernorm_f16in(const void* x, const float* gamma, const float* beta, int M, int D, float* out, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  if ((D & 127) || D > 1280) return cudaErrorInvalidValue;
+  layernorm_reg_kernel<float, __half><<<(M + 7) / 8, 256, 0, st>>>((const __half*)x, gamma, beta, M, D, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, int M, int D, void* out,
@@ -558,7 +577,8 @@ struct RowTail {
   }
 };
 
-__global__ void __launch_bounds__(128) group_mean_kernel(const float* __restrict__ x, int win, int D, float* __restrict__ out,
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(128) group_mean_kernel(const InT* __restrict__ x, int win, int D, OutT* __restrict__ out,
                                                          long long out_stride, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   const int g = blockIdx.x;
   const float inv = 1.0f / (float)win;
@@ -566,20 +586,24 @@ __global__ void __launch_bounds__(128) group_mean_kernel(const float* __restrict
   for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < win; ++r) {
-      const float4 v = *reinterpret_cast<const float4*>(x + ((long long)g * win + r) * D + e);
+      const float4 v = ldrow4(x + ((long long)g * win + r) * D + e);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
     a = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
-    *reinterpret_cast<float4*>(out + (long long)g * out_stride + e) = a;
+    strow4(out + (long long)g * out_stride + e, a);
     if (stats) tail.put(a, e, xb ? xb + (long long)g * D : nullptr);
   }
   if (stats) tail.finish(stats + g);
 }
 
-cudaError_t launch_group_mean(const float* x, int n_groups, int win, int D, float* out, long long out_stride, cudaStream_t st,
-                              __nv_bfloat16* xb, float* stats) {
+cudaError_t launch_group_mean(const void* x, bool in_f16, int n_groups, int win, int D, void* out, bool out_f16, long long out_stride,
+                              cudaStream_t st, __nv_bfloat16* xb, float* stats) {
   if (n_groups <= 0) return cudaSuccess;
-  group_mean_kernel<<<n_groups, 128, 0, st>>>(x, win, D, out, out_stride, xb, reinterpret_cast<float2*>(stats));
+  float2* s2 = reinterpret_cast<float2*>(stats);
+  if (!in_f16 && !out_f16) group_mean_kernel<float, float><<<n_groups, 128, 0, st>>>((const float*)x, win, D, (float*)out, out_stride, xb, s2);
+  else if (in_f16 && out_f16) group_mean_kernel<__half, __half><<<n_groups, 128, 0, st>>>((const __half*)x, win, D, (__half*)out, out_stride, xb, s2);
+  else if (in_f16) group_mean_kernel<__half, float><<<n_groups, 128, 0, st>>>((const __half*)x, win, D, (float*)out, out_stride, xb, s2);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
@@ -640,8 +664,9 @@ cudaError_t launch_pool20_bf16(const __nv_bfloat16* xb, int B, int T, int D, int
   return cudaGetLastError();
 }
 
+template <typename OutT>
 __global__ void __launch_bounds__(128) head_gather_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
-                                   int S, int D, float* __restrict__ out, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
+                                   int S, int D, OutT* __restrict__ out, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   // out row = ((b*S + s)*L + l)*dw + tau
   long long r = blockIdx.x;
   const int tau = (int)(r % dw); r /= dw;
@@ -649,19 +674,19 @@ __global__ void __launch_bounds__(128) head_gather_kernel(const float* __restric
   const int s = (int)(r % S);
   const int b = (int)(r / S);
   const int t = s * dw + tau;
-  float* o = out + (long long)blockIdx.x * D;
+  OutT* o = out + (long long)blockIdx.x * D;
   __nv_bfloat16* xr = xb ? xb + (long long)blockIdx.x * D : nullptr;
   RowTail tail;
   if (t < Tp) {
     const float* src = pooled + (((long long)b * L + l) * Tp_total + t_start + t) * D;
     for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
       const float4 v = *reinterpret_cast<const float4*>(src + e);
-      *reinterpret_cast<float4*>(o + e) = v;
+      strow4(o + e, v);
       if (stats) tail.put(v, e, xr);
     }
   } else {                                                        // zero rows of a ragged last window: LN of zeros = beta
     for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
-      *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      strow4(o + e, make_float4(0.f, 0.f, 0.f, 0.f));
       if (stats) tail.put(make_float4(0.f, 0.f, 0.f, 0.f), e, xr);
     }
   }
@@ -669,29 +694,31 @@ __global__ void __launch_bounds__(128) head_gather_kernel(const float* __restric
 }
 
 cudaError_t launch_head_gather(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                               float* out, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
+                               void* out, bool out_f16, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
   const long long rows = (long long)B * S * L * dw;
   if (rows <= 0) return cudaSuccess;
-  head_gather_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, out, xb, reinterpret_cast<float2*>(stats));
+  if (out_f16) head_gather_kernel<__half><<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, (__half*)out, xb, reinterpret_cast<float2*>(stats));
+  else head_gather_kernel<float><<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, (float*)out, xb, reinterpret_cast<float2*>(stats));
   return cudaGetLastError();
 }
 
 // Layer reduction of the baseline heads (models.py:113-167): mean over layers, last layer, or the learned layer weights
 // divided by their sum; rows of a ragged last window are zero like head_gather's.
+template <typename OutT>
 __global__ void __launch_bounds__(128) head_layer_reduce_kernel(const float* __restrict__ pooled, int L, int Tp_total, int t_start, int Tp, int dw,
-                                         int S, int D, int kind, const float* __restrict__ w, float* __restrict__ out,
+                                         int S, int D, int kind, const float* __restrict__ w, OutT* __restrict__ out,
                                          __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats) {
   long long r = blockIdx.x;
   const int tau = (int)(r % dw); r /= dw;
   const int s = (int)(r % S);
   const int b = (int)(r / S);
   const int t = s * dw + tau;
-  float* o = out + (long long)blockIdx.x * D;
+  OutT* o = out + (long long)blockIdx.x * D;
   __nv_bfloat16* xr = xb ? xb + (long long)blockIdx.x * D : nullptr;
   RowTail tail;
   if (t >= Tp) {
     for (int e = threadIdx.x * 4; e < D; e += blockDim.x * 4) {
-      *reinterpret_cast<float4*>(o + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      strow4(o + e, make_float4(0.f, 0.f, 0.f, 0.f));
       if (stats) tail.put(make_float4(0.f, 0.f, 0.f, 0.f), e, xr);
     }
     if (stats) tail.finish(stats + blockIdx.x);
@@ -714,19 +741,21 @@ __global__ void __launch_bounds__(128) head_layer_reduce_kernel(const float* __r
       const float inv = kind == 2 ? 1.0f / wsum : 1.0f / (float)L;
       a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
     }
-    *reinterpret_cast<float4*>(o + e) = a;
+    strow4(o + e, a);
     if (stats) tail.put(a, e, xr);
   }
   if (stats) tail.finish(stats + blockIdx.x);
 }
 
 cudaError_t launch_head_layer_reduce(const float* pooled, int B, int L, int Tp_total, int t_start, int Tp, int dw, int S, int D,
-                                     int kind, const float* w, float* out, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
+                                     int kind, const float* w, void* out, bool out_f16, cudaStream_t st, __nv_bfloat16* xb, float* stats) {
   const long long rows = (long long)B * S * dw;
   if (rows <= 0) return cudaSuccess;
   if (kind == 2 && !w) return cudaErrorInvalidValue;
-  head_layer_reduce_kernel<<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, out, xb,
-                                                          reinterpret_cast<float2*>(stats));
+  if (out_f16) head_layer_reduce_kernel<__half><<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, (__half*)out, xb,
+                                                                                  reinterpret_cast<float2*>(stats));
+  else head_layer_reduce_kernel<float><<<(unsigned)rows, 128, 0, st>>>(pooled, L, Tp_total, t_start, Tp, dw, S, D, kind, w, (float*)out, xb,
+                                                                      reinterpret_cast<float2*>(stats));
   return cudaGetLastError();
 }
 

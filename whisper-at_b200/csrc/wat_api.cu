@@ -44,10 +44,11 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 enum ProfClass { PC_MEL = 0, PC_LAYOUT, PC_GEMM, PC_ATTN, PC_LN, PC_POOL, PC_HEAD_ATTN, PC_MEAN,
-                 PC_GEMM_QKV, PC_GEMM_OUT, PC_GEMM_FC1, PC_GEMM_FC2, PC_COUNT };
-// "gemm" = conv stem, head and classifier GEMMs; the four encoder-block GEMMs have their own classes
+                 PC_GEMM_QKV, PC_GEMM_OUT, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_HEAD, PC_COUNT };
+// "gemm" = conv stem GEMMs; "gemm_head" = every GEMM of the TL-TR head incl. the classifier; the four encoder-block GEMMs have
+// their own classes
 const char* const kProfNames[PC_COUNT] = {"mel", "layout", "gemm", "attention", "layernorm", "pool", "head_attention", "mean",
-                                          "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2"};
+                                          "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2", "gemm_head"};
 
 struct ProfRec { int cls; cudaEvent_t a, b; };
 
@@ -130,6 +131,7 @@ struct wat_handle {
   std::vector<ProfRec> prof;
   size_t prof_used = 0;
   int prof_override = -1;                            // class of the next launch (encoder GEMM kinds)
+  bool in_head = false;                              // run_head is executing: its GEMMs are profiled as "gemm_head"
 };
 
 namespace {
@@ -154,6 +156,7 @@ int prof_begin(wat_handle* h, const char* what) {
   }
   const int i = (int)h->prof_used++;
   h->prof[i].cls = h->prof_override >= 0 ? h->prof_override : prof_class(what);
+  if (h->in_head && h->prof[i].cls == PC_GEMM) h->prof[i].cls = PC_GEMM_HEAD;
   h->prof_override = -1;
   cudaEventRecord(h->prof[i].a, h->cur_stream);
   return i;
@@ -417,12 +420,15 @@ int run_block_f32(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bo
 
 // fp32-output GEMM of the bf16 path whose output rows feed a LayerNorm: besides C (= R + act(A W^T + bias)) the epilogue
 // leaves the rows' bf16 copy in h->xn and their (sum, sum of squares) slices in h->stats; returns the slice count in *np
-int gemm_producer(wat_handle* h, const void* A, int64_t lda, const __nv_bfloat16* W, const float* bias, float* C, const float* R,
-                  int64_t ldr, int r_mod, int M, int N, int K, int act, cudaStream_t st, int* np) {
+// The residual stream C is kept in fp16 in bf16 mode (the dtype of the reference's own GPU path; the arithmetic of the epilogue
+// is fp32): r_f16 says whether R is that stream (true) or an fp32 table such as the positional embedding (false).
+int gemm_producer(wat_handle* h, const void* A, int64_t lda, const __nv_bfloat16* W, const float* bias, void* C, const void* R,
+                  bool r_f16, int64_t ldr, int r_mod, int M, int N, int K, int act, cudaStream_t st, int* np) {
   GemmTc g;
   memset(&g, 0, sizeof(g));
-  g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = N; g.R = R; g.ldr = ldr; g.r_mod = r_mod;
+  g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = N; g.R = (const float*)R; g.ldr = ldr; g.r_mod = r_mod;
   g.M = M; g.N = N; g.K = K; g.act = act; g.epi = R ? TC_EPI_F32_RES : TC_EPI_F32;
+  g.c_f16 = 1; g.r_f16 = r_f16 ? 1 : 0;
   g.xb = (__nv_bfloat16*)h->xn.p; g.ldxb = N;
   g.stats = (float*)h->stats.p; g.stats_np = gemm_tc_stats_slices(M, N, K, g.epi, 0);
   *np = g.stats_np;
@@ -431,10 +437,11 @@ int gemm_producer(wat_handle* h, const void* A, int64_t lda, const __nv_bfloat16
 }
 
 // The same block in bf16 mode.  No LayerNorm kernel runs: x arrives with its bf16 copy in h->xn and `np` statistics slices in
-// h->stats (left by whatever produced x), both LayerNorms are folded into the QKV / fc1 GEMMs, and the out-proj / fc2
+// h->stats (left by whatever produced x; x itself is the fp16 residual stream), both LayerNorms are folded into the QKV / fc1
+// GEMMs, and the out-proj / fc2
 // epilogues leave the same by-products for the next consumer.  An encoder layer's 20x pooled state (model.py:171-174) is taken
 // from the bf16 copy fc2 leaves (pool20_bf16_kernel).
-int run_block_bf16(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, bool encoder, cudaStream_t st, int* np,
+int run_block_bf16(wat_handle* h, const BlockW& w, void* x, int n_seq, int T, bool encoder, cudaStream_t st, int* np,
                    float* pooled = nullptr, int pool_layer = -1) {
   const int D = w.D, rows = n_seq * T;
   int rc;
@@ -457,7 +464,7 @@ int run_block_bf16(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, b
     KL(h, launch_attn_small(h->qkv.p, true, h->att.p, true, n_seq, T, w.H, D / w.H, st));
   }
   if (encoder) h->prof_override = PC_GEMM_OUT;
-  if ((rc = gemm_producer(h, h->att.p, D, w.wo_h, w.bo, x, x, D, 0, rows, D, D, 0, st, np))) return rc;
+  if ((rc = gemm_producer(h, h->att.p, D, w.wo_h, w.bo, x, x, true, D, 0, rows, D, D, 0, st, np))) return rc;
   memset(&g, 0, sizeof(g));
   g.A = (const __nv_bfloat16*)h->xn.p; g.lda = D; g.W = w.w1_h; g.bias = w.b1_f; g.C = h->hbuf.p; g.ldc = 4 * D;
   g.M = rows; g.N = 4 * D; g.K = D; g.act = 1; g.epi = TC_EPI_BF16;
@@ -465,7 +472,7 @@ int run_block_bf16(wat_handle* h, const BlockW& w, float* x, int n_seq, int T, b
   if (encoder) h->prof_override = PC_GEMM_FC1;
   KL(h, launch_gemm_tc(g, h->num_sms, st));
   if (encoder) h->prof_override = PC_GEMM_FC2;
-  if ((rc = gemm_producer(h, h->hbuf.p, 4 * D, w.w2_h, w.b2, x, x, D, 0, rows, D, 4 * D, 0, st, np))) return rc;
+  if ((rc = gemm_producer(h, h->hbuf.p, 4 * D, w.w2_h, w.b2, x, x, true, D, 0, rows, D, 4 * D, 0, st, np))) return rc;
   if (pooled && pool_layer >= 0) KL(h, launch_pool20_bf16((const __nv_bfloat16*)h->xn.p, n_seq, T, D, pool_layer, h->L, pooled, st));
   return 0;
 }
@@ -483,7 +490,7 @@ int run_encoder(wat_handle* h, int B, float* pooled, float* x_out, cudaStream_t 
   KL(h, launch_im2col_k3(h->qkv.p, h->bf16, B, 3000, d, 2, 1500, h->hbuf.p, st));
   if (h->bf16) {
     int np = 0;
-    if ((rc = gemm_producer(h, h->hbuf.p, 3 * d, h->conv2_w_h, h->conv2_b, x, h->pos, d, 1500, B * 1500, d, 3 * d, 1, st, &np))) return rc;
+    if ((rc = gemm_producer(h, h->hbuf.p, 3 * d, h->conv2_w_h, h->conv2_b, x, h->pos, false, d, 1500, B * 1500, d, 3 * d, 1, st, &np))) return rc;
     for (int l = 0; l < h->L; ++l)
       if ((rc = run_block_bf16(h, h->enc[l], x, B, 1500, true, st, &np, pooled, l))) return rc;
   } else {
@@ -493,12 +500,24 @@ int run_encoder(wat_handle* h, int B, float* pooled, float* x_out, cudaStream_t 
       if ((rc = run_block_f32(h, h->enc[l], x, B, 1500, true, st, pooled, l - 1))) return rc;
     KL(h, launch_pool20(x, B, 1500, d, h->L - 1, h->L, pooled, st));   // last layer: nothing downstream reads x again
   }
-  if (x_out) KL(h, launch_layernorm(x, h->lnp_g, h->lnp_b, B * 1500, d, x_out, false, st));
+  if (x_out) {
+    if (h->bf16) KL(h, launch_layernorm_f16in(x, h->lnp_g, h->lnp_b, B * 1500, d, x_out, st));
+    else KL(h, launch_layernorm(x, h->lnp_g, h->lnp_b, B * 1500, d, x_out, false, st));
+  }
   return 0;
 }
 
+int run_head_impl(wat_handle* h, const float* pooled, int B, int t_total, int t_start, int t_len, int dw, float* logits,
+                  cudaStream_t st);
 int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start, int t_len, int dw, float* logits,
              cudaStream_t st) {
+  h->in_head = true;
+  const int rc = run_head_impl(h, pooled, B, t_total, t_start, t_len, dw, logits, st);
+  h->in_head = false;
+  return rc;
+}
+int run_head_impl(wat_handle* h, const float* pooled, int B, int t_total, int t_start, int t_len, int dw, float* logits,
+                  cudaStream_t st) {
   const int d = h->d, di = h->di, L = h->L, nc = h->cfg.n_class;
   if (dw < 1 || dw > 128) return fail(WAT_ERR_INVALID, "decision window %d out of range [1,128]", dw);
   if (t_len < 1 || t_len > (h->head_only ? 128 : 75) || t_start < 0 || t_start + t_len > t_total) return fail(WAT_ERR_INVALID, "bad pooled slice");
@@ -517,6 +536,10 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
     const int rows = (int)(nb * rows_clip);
     const float* pin = pooled + (int64_t)b0 * L * t_total * d;
     float* src0 = head_has_down(mode) ? x2 : x;                   // regrouped input; the down-projection lands in x
+    // bf16 mode: the rows a transformer block works on (x, and x2 for the layer transformer) are the fp16 residual stream; the
+    // regrouped input of the down-projection's LayerNorm kernel and the final means (lmean) stay fp32
+    const bool f16 = h->bf16;
+    const bool src_f16 = f16 && !head_has_down(mode) && head_has_time_tr(mode);
     // bf16 mode: whoever produces the rows a transformer block starts from also leaves their bf16 copy (h->xn) and their
     // LayerNorm statistics (h->stats, `np` slices) - see run_block_bf16.  The down-projection's own LayerNorm stays a kernel.
     const bool fold = h->bf16 && head_has_time_tr(mode);
@@ -525,36 +548,38 @@ int run_head(wat_handle* h, const float* pooled, int B, int t_total, int t_start
     float* stats = (float*)h->stats.p;
     int np = 1;
     if (layerwise) {
-      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, src0, st, fold_src ? xb : nullptr, fold_src ? stats : nullptr));
+      KL(h, launch_head_gather(pin, nb, L, t_total, t_start, t_len, dw, S, d, src0, src_f16, st, fold_src ? xb : nullptr, fold_src ? stats : nullptr));
     } else {                                                      // baselines: the layer axis is reduced first (models.py:113-167)
       const int kind = (mode == WAT_HEAD_LAST_MLP || mode == WAT_HEAD_LAST_TR) ? 1 : head_has_layer_w(mode) ? 2 : 0;
-      KL(h, launch_head_layer_reduce(pin, nb, L, t_total, t_start, t_len, dw, S, d, kind, h->layer_w, src0, st,
+      KL(h, launch_head_layer_reduce(pin, nb, L, t_total, t_start, t_len, dw, S, d, kind, h->layer_w, src0, src_f16, st,
                                      fold_src ? xb : nullptr, fold_src ? stats : nullptr));
     }
     if (head_has_down(mode)) {
       KL(h, launch_layernorm(x2, h->down_g, h->down_b, rows, d, h->xn.p, h->bf16, st));
       if (h->bf16) {
-        if ((rc = gemm_producer(h, h->xn.p, d, h->down_w_h, h->down_bias, x, nullptr, 0, 0, rows, di, d, 0, st, &np))) return rc;
+        if ((rc = gemm_producer(h, h->xn.p, d, h->down_w_h, h->down_bias, x, nullptr, false, 0, 0, rows, di, d, 0, st, &np))) return rc;
       } else if ((rc = gemm(h, h->xn.p, d, h->down_w, h->down_w_h, h->down_bias, x, di, nullptr, 0, 0, rows, di, d, 0, true, st))) return rc;
     }
     if (layerwise) {
       if (h->bf16) {
         if ((rc = run_block_bf16(h, h->time_tr, x, nb * S * L, dw, false, st, &np))) return rc;
-        KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st, xb, stats));
+        KL(h, launch_group_mean(x, true, nb * S * L, dw, di, x2, true, di, st, xb, stats));
         np = 1;
         if ((rc = run_block_bf16(h, h->layer_tr, x2, nb * S, L, false, st, &np))) return rc;
       } else {
         if ((rc = run_block_f32(h, h->time_tr, x, nb * S * L, dw, false, st))) return rc;
-        KL(h, launch_group_mean(x, nb * S * L, dw, di, x2, di, st));
+        KL(h, launch_group_mean(x, false, nb * S * L, dw, di, x2, false, di, st));
         if ((rc = run_block_f32(h, h->layer_tr, x2, nb * S, L, false, st))) return rc;
       }
-      KL(h, launch_group_mean(x2, nb * S, L, di, (float*)h->lmean.p, di, st));
+      KL(h, launch_group_mean(x2, f16, nb * S, L, di, h->lmean.p, false, di, st));
     } else {
       if (head_has_time_tr(mode)) {
         if (h->bf16) { if ((rc = run_block_bf16(h, h->time_tr, x, nb * S, dw, false, st, &np))) return rc; }
         else if ((rc = run_block_f32(h, h->time_tr, x, nb * S, dw, false, st))) return rc;
       }
-      KL(h, launch_group_mean(x, nb * S, dw, di, (float*)h->lmean.p, di, st));
+      // x is fp16 only when a transformer block (or the bf16 down-projection) wrote it; the *_mlp baselines read the fp32 rows
+      const bool x_f16 = f16 && (head_has_time_tr(mode) || head_has_down(mode));
+      KL(h, launch_group_mean(x, x_f16, nb * S, dw, di, h->lmean.p, false, di, st));
     }
     KL(h, launch_layernorm((const float*)h->lmean.p, h->cls_g, h->cls_b, nb * S, di, h->lnout.p, false, st));
     GemmF32 g;
@@ -1047,15 +1072,16 @@ int wat_dbg_gemm_bf16(const void* A, const void* W, const float* bias, void* C, 
 }
 
 // LayerNorm folded into its consumer, as run_block_bf16 chains it (all pointers device):
-//   producer  x = R + A1 W1^T + bias1            A1 [M,K1] bf16, W1 [D,K1] bf16, R / x [M,D] fp32; the epilogue also writes
+//   producer  x = R + A1 W1^T + bias1            A1 [M,K1] bf16, W1 [D,K1] bf16, R / x [M,D] fp32 (fp16 when x_f16: how the
+//             bf16 encoder keeps its residual stream); the epilogue also writes
 //             xb [M,D] bf16 and stats [M, np, 2] (np = return value of wat_dbg_ln_slices); if pooled != NULL (M % 1500 == 0),
 //             pooled [M/1500, 1, 75, D] = 20-row means of xb (pool20_bf16_kernel, as the encoder takes them)
 //   consumer  out [M,N2] bf16 = act(LN(x; gamma, beta) W2^T + bias2) computed as rstd (xb W2'^T - mean colsum) + bias2'
 // pair: 1 = CTA-pair kernels, -1 = single-CTA kernels.
 int wat_dbg_ln_slices(int32_t M, int32_t D, int32_t K1, int32_t pair) { return gemm_tc_stats_slices(M, D, K1, TC_EPI_F32_RES, pair); }
-int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const float* R, float* x, void* xb, float* stats, float* pooled,
+int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const void* R, void* x, void* xb, float* stats, float* pooled,
                     const float* W2, const float* gamma, const float* beta, const float* bias2, void* out, int32_t M, int32_t D,
-                    int32_t K1, int32_t N2, int32_t act, int32_t pair, void* stream) {
+                    int32_t K1, int32_t N2, int32_t act, int32_t pair, int32_t x_f16, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   CU(cudaGetDevice(&dev));
@@ -1068,7 +1094,8 @@ int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const fl
   cudaError_t e = launch_fold_ln_weights(W2, gamma, beta, bias2, N2, D, W2h, cs, b2f, st);
   GemmTc g;
   memset(&g, 0, sizeof(g));
-  g.A = (const __nv_bfloat16*)A1; g.lda = K1; g.W = (const __nv_bfloat16*)W1; g.bias = bias1; g.C = x; g.ldc = D; g.R = R; g.ldr = D;
+  g.A = (const __nv_bfloat16*)A1; g.lda = K1; g.W = (const __nv_bfloat16*)W1; g.bias = bias1; g.C = x; g.ldc = D; g.R = (const float*)R; g.ldr = D;
+  g.c_f16 = g.r_f16 = x_f16 ? 1 : 0;                              // R and x in fp16: the bf16 mode's residual stream
   g.M = M; g.N = D; g.K = K1; g.epi = TC_EPI_F32_RES; g.force_pair = pair;
   g.xb = (__nv_bfloat16*)xb; g.ldxb = D; g.stats = stats; g.stats_np = gemm_tc_stats_slices(M, D, K1, TC_EPI_F32_RES, pair);
   if (e == cudaSuccess) e = launch_gemm_tc(g, sms, st);

@@ -65,7 +65,7 @@ _SIGS = {
     "wat_dbg_gemm": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_gemm_bf16": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_ln_slices": (C.c_int, [_i32, _i32, _i32, _i32]),
-    "wat_dbg_ln_gemm": (C.c_int, [_fp] * 13 + [_i32] * 6 + [_vp]),
+    "wat_dbg_ln_gemm": (C.c_int, [_fp] * 13 + [_i32] * 7 + [_vp]),
     "wat_dbg_attention": (C.c_int, [_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _vp]),
     "wat_dbg_attention_repeats": (C.c_int, []),
     "wat_dbg_tma_overlap_probe": (C.c_int, []),
