@@ -11,7 +11,8 @@ on (config 5): large-v2 + full TL-TR head, 128-bin mel, at_time_res=10, 128 clip
 512 clips over the ranks, 256 on one GPU).  Rank 0 prints ONE JSON line; see DESIGN.md §Measurement for every field.
 
 Arms:  ours        the repo's CUDA path (value: inputs resident in HBM; e2e: host buffers through wat_tag_host)
-       reference   the reference's CPU path (oracle port, torch CPU fp32, all host threads), rank 0 only
+       reference   the reference's CPU path (the reference package itself from oracle/_ref when present, else the oracle
+                   port; torch CPU fp32, all host threads), rank 0 only
        torch_eager the same path in PyTorch eager ops on the GPU (baseline/torch_eager.py: cuBLASLt, cuDNN, SDPA)
 The `ours` line also carries `cpu_baseline` (bounded sample of the CPU arm) and `gpu_baseline` (the torch-eager arm
 on the same workload, same box, same run).
@@ -116,23 +117,61 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def oracle_time_clips(name, n_mels, low, res, n_clips, threads):
-    """The CPU arm: the oracle port of the reference (oracle/wat_oracle.py), fp32, one clip per call as the
-    reference's AT output requires, on `threads` host threads.  Returns seconds per clip (list)."""
+def oracle_time_clips(name, n_mels, low, res, n_clips, threads, return_logits=False):
+    """The oracle port of the reference (oracle/wat_oracle.py), fp32, one clip per call as the reference's AT output
+    requires, on `threads` host threads.  Returns seconds per clip (list)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import wat_oracle as O
     from whisper_at import synth
     torch.set_num_threads(threads)
     d, h, L = synth.MODEL_SHAPES[name]
     sd = synth.synth_state_dict(n_mels, d, L, low, seed=1, init="lively")
-    times = []
+    times, first = [], None
     with torch.no_grad():
         for i in range(n_clips):
             clip = synth.synth_clip(1 + i)
             t0 = time.perf_counter()
-            O.tag(clip[None], sd, h, n_mels, res)
+            lg = O.tag(clip[None], sd, h, n_mels, res)
             times.append(time.perf_counter() - t0)
-    return times
+            if first is None:
+                first = lg[0]
+    return (times, first) if return_logits else times
+
+
+def reference_time_clips(name, n_mels, low, res, n_clips, threads):
+    """The REFERENCE ITSELF (oracle/_ref/whisper_at, an unmodified copy placed by oracle/make_ref.py) on the host cores,
+    run by oracle/ref_runner.py in its own interpreter because the product package carries the same module name.
+    Returns (seconds per clip, logits of the first clip) or None when oracle/_ref is not on this box."""
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "whisper_at", "model.py")):
+        return None
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--name", name, "--n-mels", str(n_mels),
+           "--low", str(int(low)), "--res", str(res), "--clips", str(n_clips), "--threads", str(threads)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0:
+        print("reference runner failed:", r.stderr[-2000:], file=sys.stderr)
+        return None
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return d["times"], torch.tensor(d["logits"], dtype=torch.float32)
+
+
+def cpu_arm(name, n_mels, low, res, budget_s, max_clips, threads):
+    """Times the reference's CPU path on a bounded sample: one warm-up clip sizes the run, then up to `max_clips` clips
+    within ~budget_s.  Uses the reference itself when oracle/_ref travelled to this box (kind "reference", checked
+    against the oracle port on the first clip), else the oracle port (kind "port")."""
+    t_first, lg_port = oracle_time_clips(name, n_mels, low, res, 1, threads, return_logits=True)
+    n = max(1, min(max_clips, int(budget_s / max(t_first[0], 1e-3))))
+    ref = reference_time_clips(name, n_mels, low, res, n + 1, threads)
+    if ref is not None:
+        times, lg_ref = ref
+        times = times[1:]                                           # its first clip is the warm-up
+        diff = float((lg_ref.reshape(lg_port.shape) - lg_port).abs().max())
+        assert diff <= 2e-4, f"oracle port and reference disagree on the first clip: {diff}"
+        return dict(times=times, kind="reference", port_max_abs_diff=diff,
+                    how="the unmodified reference package (oracle/_ref/whisper_at via oracle/ref_runner.py: log_mel_spectrogram -> "
+                        "AudioEncoder -> at_model), torch CPU fp32")
+    times = oracle_time_clips(name, n_mels, low, res, n, threads)
+    return dict(times=times, kind="port", port_max_abs_diff=None, how="oracle/wat_oracle.py (port; oracle/_ref absent), torch CPU fp32")
 
 
 def time_torch_eager(sd, n_head, n_mels, audio_dev, audio_host, res, steps, warmup, ours_logits=None):
@@ -229,17 +268,16 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        budget = 240.0
-        t_first = oracle_time_clips(name, n_mels, low, res, 1, threads)[0]       # warm-up step (also sizes the run)
-        steps = max(1, min(args.steps, int((budget - t_first) / max(t_first, 1e-3))))
-        times = oracle_time_clips(name, n_mels, low, res, steps, threads)
+        arm = cpu_arm(name, n_mels, low, res, 200.0, args.steps, threads)
+        times = arm["times"]
+        steps = len(times)
         total = sum(times)
         val = 30.0 * steps / total
         out = dict(metric=metric, value=val, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=1, ms_per_step=1000 * total / steps,
                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                    config=dict(config, clips_per_step=1, steps_requested=args.steps),
-                   cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port",
-                                     sample=f"{steps} step(s) of 1 clip each (the reference's AT path is batch-1), oracle/wat_oracle.py, torch CPU fp32"),
+                   cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind=arm["kind"], port_max_abs_diff=arm["port_max_abs_diff"],
+                                     sample=f"{steps} step(s) of 1 clip each (the reference's AT path is batch-1), {arm['how']}"),
                    e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out))
         return
@@ -457,12 +495,12 @@ def main():
                                             "linear + F.scaled_dot_product_attention (and the reference's materialised-qk attention), bf16")
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            tt = oracle_time_clips(name, n_mels, low, res, 1, threads)          # first clip also warms torch up
-            n_more = max(1, min(8, int(15.0 / max(tt[0], 1e-3))))                                # ~15 s of CPU work
-            tt = oracle_time_clips(name, n_mels, low, res, n_more, threads)
-            out["cpu_baseline"] = dict(value=30.0 * len(tt) / sum(tt), unit=UNIT, cores=threads, kind="port",
+            arm = cpu_arm(name, n_mels, low, res, 15.0, 8, threads)                              # ~15 s of CPU work
+            tt = arm["times"]
+            out["cpu_baseline"] = dict(value=30.0 * len(tt) / sum(tt), unit=UNIT, cores=threads, kind=arm["kind"],
+                                       port_max_abs_diff=arm["port_max_abs_diff"],
                                        sample=f"{len(tt)} clips of the same workload (after 1 warm-up clip), one per call as the "
-                                              "reference's AT path requires, oracle/wat_oracle.py (torch CPU fp32), all host threads")
+                                              f"reference's AT path requires, {arm['how']}, all host threads")
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
