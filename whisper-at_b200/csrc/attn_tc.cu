@@ -513,6 +513,9 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   // Measured without gain on top of this kernel (round 2): loading S from TMEM in two halves with the second load in flight
   // during the first half's exponentials, and asking for PV(j-1)'s completion at the start of the step (79.6-81.8 ms vs 81.0
   // on the same box) - the per-step latencies are hidden by the three co-resident CTAs, not exposed.
+  // One elected mbarrier arrival per softmax warp (barrier counts 4 instead of 128; both arrivals follow a warp-collective
+  // tcgen05.wait) was measured too: 81.5-82.3 ms against 78.8-79.0 ms on the same box - the __syncwarp and the divergent
+  // branch cost more than the 32 per-thread arrivals they replace.
   // HALVES = 2 (two threads per query row in the max-free pass, 9 warps per CTA) is implemented above and was measured:
   // 94 ms per step against 81 ms for one thread per row on the same box - more warps per step cost more in hand-overs and
   // registers (72 per thread) than the shorter per-thread exponential phase gains.  Only HALVES = 1 is instantiated.
