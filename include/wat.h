@@ -144,6 +144,18 @@ WAT_API int wat_tag_pcm16(wat_handle* h, const int16_t* pcm, int64_t clip_stride
 WAT_API int wat_tag_host_pcm16(wat_handle* h, const int16_t* pcm_host, int64_t clip_stride, const int32_t* n_valid,
                                int32_t n_samples, int32_t B, int32_t dw, float* logits_host);
 
+/* Pipelined host entry points: wat_tag_host == submit + wait.  submit returns as soon as the work is queued (H2D of the PCM on a
+ * copy stream into one of two device stages, compute on the handle's stream, D2H of the logits behind it); wait blocks until
+ * that call's logits are in logits_host.  With  submit(t+1); wait(t);  in a loop the PCM of the next call crosses PCIe while
+ * the current one computes.  pcm_host and logits_host must stay valid (and should be pinned) until the ticket has been waited
+ * for; a third submit first waits for the call two tickets back.  Tickets are per handle, start at 1, and waiting twice is
+ * harmless.  (This is the double buffering the reference's DataLoader + .to(device) would do for a GPU run; transcribe.py:128.) */
+WAT_API int wat_tag_host_submit(wat_handle* h, const float* pcm_host, int64_t clip_stride, const int32_t* n_valid,
+                                int32_t n_samples, int32_t B, int32_t dw, float* logits_host, int64_t* ticket);
+WAT_API int wat_tag_host_submit_pcm16(wat_handle* h, const int16_t* pcm_host, int64_t clip_stride, const int32_t* n_valid,
+                                      int32_t n_samples, int32_t B, int32_t dw, float* logits_host, int64_t* ticket);
+WAT_API int wat_tag_host_wait(wat_handle* h, int64_t ticket);
+
 /* introspection */
 WAT_API int64_t wat_workspace_bytes(const wat_handle* h);
 WAT_API int64_t wat_kernel_launches(const wat_handle* h);   /* kernels launched by this handle since creation */

@@ -625,6 +625,45 @@ def test_host_entry_point_pieces_span_chunks():
     assert torch.equal(m.tag_batch_host(pcm16, at_time_res=10), m.tag_batch(pcm16.cuda(), at_time_res=10).cpu())
 
 
+def test_pipelined_host_calls_equal_the_synchronous_ones():
+    """wat_tag_host_submit / wait: two calls in flight on alternating PCM stages give exactly the logits of the blocking
+    entry point, whatever mix of batch sizes, sample types and n_valid shares the pipeline; a third submit re-uses the
+    stage of the first (and so waits for it); waiting twice or out of order is harmless; unknown tickets are refused."""
+    import ctypes as C
+    m, sd, h = model_for("tiny", seed=1, init="lively", precision="bf16", max_batch=16)
+    a = synth.synth_batch(20, start=3).pin_memory()               # 20 clips: 8 PCM pieces, 2 internal chunks
+    b = synth.synth_batch(3, start=11).pin_memory()
+    c16 = (synth.synth_batch(5, start=30).clamp(-1, 1) * 32767).round().to(torch.int16).pin_memory()
+    nv = np.array([480000, 16000, 250000], dtype=np.int32)
+    want = [m.tag_batch_host(a, at_time_res=10), m.tag_batch_host(b, at_time_res=2, n_valid=nv),
+            m.tag_batch_host(c16, at_time_res=10)]
+    # classic two-deep pipeline, twice around so both stages are re-used
+    outs, pend = [], None
+    for rep in range(2):
+        for x, kw in ((a, dict(at_time_res=10)), (b, dict(at_time_res=2, n_valid=nv)), (c16, dict(at_time_res=10))):
+            nxt = m.tag_batch_host_async(x, **kw)
+            if pend is not None:
+                outs.append(pend.result())
+            pend = nxt
+    outs.append(pend.result())
+    for i, o in enumerate(outs):
+        assert torch.equal(o, want[i % 3]), i
+    # three submits without a wait in between, results taken in reverse order, one of them twice
+    p1 = m.tag_batch_host_async(a, at_time_res=10)
+    p2 = m.tag_batch_host_async(b, at_time_res=2, n_valid=nv)
+    p3 = m.tag_batch_host_async(c16, at_time_res=10)
+    assert torch.equal(p3.result(), want[2]) and torch.equal(p2.result(), want[1])
+    assert torch.equal(p1.result(), want[0]) and torch.equal(p1.result(), want[0])
+    # interleaved with the device entry point on torch's stream (shared workspace, ordered by events)
+    p4 = m.tag_batch_host_async(a, at_time_res=10)
+    dev = m.tag_batch(b.cuda(), at_time_res=2, n_valid=nv).cpu()
+    assert torch.equal(dev, want[1]) and torch.equal(p4.result(), want[0])
+    eng = m.engine("bf16")
+    assert eng.L.wat_tag_host_wait(eng.h, 0) != 0 and eng.L.wat_tag_host_wait(eng.h, 10 ** 6) != 0
+    assert b"ticket" in eng.L.wat_last_error()
+    assert eng.L.wat_tag_host_wait(eng.h, 1) == 0                 # long finished
+
+
 def test_permutation_and_chunking_invariance():
     """size-independent properties: clip order and internal chunking (max_batch) do not change any clip's logits"""
     a = synth.synth_batch(5, start=1).cuda()

@@ -115,15 +115,19 @@ struct wat_handle {
   int ws_B = 0;
   int64_t rows_cap = 0;
   int head_chunk = 1;
-  Buf x, x2, xn, qkv, vt, att, hbuf, logspec, clipmax, melT, pooled, lmean, lnout, nvalid, logits, pcm_stage, stats;
+  Buf x, x2, xn, qkv, vt, att, hbuf, logspec, clipmax, melT, pooled, lmean, lnout, nvalid, logits, stats;
+  Buf pcm_stage[2];                                              // host entry points: two PCM stages, see tag_host_submit
   cudaStream_t own_stream = nullptr;
   // the workspace is shared by every call on the handle: when a call arrives on another stream than the previous one (e.g.
   // wat_tag on the caller's stream, then wat_tag_host on the handle's own stream) it is ordered after the previous call's work
   cudaStream_t last_stream = nullptr;
   bool last_stream_valid = false;
   cudaEvent_t order_ev = nullptr;
-  cudaStream_t copy_stream = nullptr;                            // wat_tag_host: H2D of PCM pieces, overlapped with the mel kernel
-  cudaEvent_t piece_ev[8] = {};
+  cudaStream_t copy_stream = nullptr;                            // wat_tag_host*: H2D of PCM pieces, overlapped with the mel kernel
+  cudaEvent_t piece_ev[2][8] = {};                               // ... per stage: piece p of the PCM has arrived
+  cudaEvent_t done_ev[2] = {};                                   // ... per stage: the call's logits are in the caller's host buffer
+  int64_t next_ticket = 1;                                       // ticket t uses stage t & 1; at most two calls in flight
+  int64_t slot_ticket[2] = {0, 0};                               // the call that owns the stage, 0 = finished / none
   int64_t ws_bytes = 0;
   // per-kernel-class timing (wat_profile)
   bool profiling = false;
@@ -700,8 +704,10 @@ int wat_create(const wat_config* cfg, wat_handle** out) {
     if (cudaMemcpy(h->pos, pos.data(), sizeof(float) * pos.size(), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "pos upload"); break; }
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "stream create"); break; }
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(WAT_ERR_CUDA, "stream create"); break; }
-    for (int i = 0; i < 8 && !rc; ++i)
-      if (cudaEventCreateWithFlags(&h->piece_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(WAT_ERR_CUDA, "event create");
+    for (int i = 0; i < 16 && !rc; ++i)
+      if (cudaEventCreateWithFlags(&h->piece_ev[i / 8][i % 8], cudaEventDisableTiming) != cudaSuccess) rc = fail(WAT_ERR_CUDA, "event create");
+    for (int i = 0; i < 2 && !rc; ++i)
+      if (cudaEventCreateWithFlags(&h->done_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(WAT_ERR_CUDA, "event create");
     if (rc) break;
   } while (0);
   if (rc) { wat_destroy(h); return rc; }
@@ -767,12 +773,13 @@ int wat_destroy(wat_handle* h) {
   cudaDeviceSynchronize();
   for (void* p : h->owned) cudaFree(p);
   Buf* bufs[] = {&h->x, &h->x2, &h->xn, &h->qkv, &h->vt, &h->att, &h->hbuf, &h->logspec, &h->clipmax, &h->melT,
-                 &h->pooled, &h->lmean, &h->lnout, &h->nvalid, &h->logits, &h->pcm_stage, &h->stats};
+                 &h->pooled, &h->lmean, &h->lnout, &h->nvalid, &h->logits, &h->pcm_stage[0], &h->pcm_stage[1], &h->stats};
   for (Buf* b : bufs) if (b->p) cudaFree(b->p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
-  for (int i = 0; i < 8; ++i) if (h->piece_ev[i]) cudaEventDestroy(h->piece_ev[i]);
+  for (int i = 0; i < 16; ++i) if (h->piece_ev[i / 8][i % 8]) cudaEventDestroy(h->piece_ev[i / 8][i % 8]);
+  for (int i = 0; i < 2; ++i) if (h->done_ev[i]) cudaEventDestroy(h->done_ev[i]);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
   return WAT_OK;
@@ -908,8 +915,13 @@ static int tag_impl(wat_handle* h, const void* pcm, bool i16, int64_t clip_strid
   return WAT_OK;
 }
 
-static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t clip_stride, const int32_t* n_valid,
-                         int32_t n_samples, int32_t B, int32_t dw, float* logits_host) {
+// Host entry points.  A call is submitted (H2D of the PCM in pieces on the copy stream, compute on the handle's own stream, D2H
+// of the logits behind it) and later waited for.  Two PCM stages alternate, so while call t computes, the PCM of call t + 1 is
+// already crossing PCIe: in a submit(t+1) / wait(t) loop the H2D copy disappears behind the previous call's compute.  The compute
+// of successive calls is serialised by the stream (they share the workspace); the device logits buffer is shared too, because
+// the D2H of call t precedes the head of call t + 1 in stream order.
+static int tag_host_submit(wat_handle* h, const void* pcm_host, bool i16, int64_t clip_stride, const int32_t* n_valid,
+                           int32_t n_samples, int32_t B, int32_t dw, float* logits_host, int64_t* ticket) {
   int rc = check_ready(h);
   if (rc) return rc;
   ON_DEVICE(h);
@@ -921,31 +933,54 @@ static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t 
       if (n_valid[i] < 0 || n_valid[i] > n_samples) return fail(WAT_ERR_INVALID, "n_valid[%d] out of range", i);
   const int S = (75 + dw - 1) / dw;
   cudaStream_t st = h->own_stream;
-  const size_t pcm_bytes = (i16 ? sizeof(int16_t) : sizeof(float)) * ((size_t)(B - 1) * clip_stride + n_samples);
-  if ((rc = grow(h, h->pcm_stage, pcm_bytes))) return rc;
-  if ((rc = grow(h, h->logits, sizeof(float) * (size_t)B * S * h->cfg.n_class))) return rc;
-  // H2D in up to 8 pieces on the copy stream (the previous call ended with a stream synchronize, so the stage is free)
+  const int slot = (int)(h->next_ticket & 1);
+  // the stage (and its events) belong to call t - 2 until that call has finished; a caller that never waited for it waits here
+  if (h->slot_ticket[slot]) { CU(cudaEventSynchronize(h->done_ev[slot])); h->slot_ticket[slot] = 0; }
   const size_t esz = i16 ? sizeof(int16_t) : sizeof(float);
+  const size_t pcm_bytes = esz * ((size_t)(B - 1) * clip_stride + n_samples);
+  if ((rc = grow(h, h->pcm_stage[slot], pcm_bytes))) return rc;
+  if ((rc = grow(h, h->logits, sizeof(float) * (size_t)B * S * h->cfg.n_class))) return rc;
   const int n_piece = B >= 16 ? 8 : 1;
   const int piece_clips = (B + n_piece - 1) / n_piece;
+  cudaEvent_t* piece_ev = h->piece_ev[slot];
   for (int p = 0; p < n_piece; ++p) {
     const int c0 = p * piece_clips, c1 = std::min(B, c0 + piece_clips);
-    if (c0 >= c1) { CU(cudaEventRecord(h->piece_ev[p], h->copy_stream)); continue; }
+    if (c0 >= c1) { CU(cudaEventRecord(piece_ev[p], h->copy_stream)); continue; }
     const size_t off = (size_t)c0 * clip_stride * esz;
     const size_t bytes = esz * ((size_t)(c1 - c0 - 1) * clip_stride + n_samples);
-    CU(cudaMemcpyAsync((char*)h->pcm_stage.p + off, (const char*)pcm_host + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-    CU(cudaEventRecord(h->piece_ev[p], h->copy_stream));
+    CU(cudaMemcpyAsync((char*)h->pcm_stage[slot].p + off, (const char*)pcm_host + off, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(piece_ev[p], h->copy_stream));
   }
-  if ((rc = tag_impl(h, h->pcm_stage.p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st, h->piece_ev, piece_clips))) {
+  if ((rc = tag_impl(h, h->pcm_stage[slot].p, i16, clip_stride, n_valid, n_samples, B, dw, (float*)h->logits.p, st, piece_ev, piece_clips))) {
     // the H2D pieces (and whatever was launched before the failure) may still be in flight: the caller is free to release
-    // pcm_host as soon as we return, and the next call reuses pcm_stage
+    // pcm_host as soon as we return, and a later call reuses the stage
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(st);
     return rc;
   }
   CU(cudaMemcpyAsync(logits_host, h->logits.p, sizeof(float) * (size_t)B * S * h->cfg.n_class, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(cudaEventRecord(h->done_ev[slot], st));
+  h->slot_ticket[slot] = h->next_ticket;
+  *ticket = h->next_ticket++;
   return WAT_OK;
+}
+
+static int tag_host_wait(wat_handle* h, int64_t ticket) {
+  if (!h) return fail(WAT_ERR_INVALID, "null handle");
+  if (ticket < 1 || ticket >= h->next_ticket) return fail(WAT_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+  const int slot = (int)(ticket & 1);
+  if (h->slot_ticket[slot] != ticket) return WAT_OK;              // waited for already, or its stage was re-used (which waits for it)
+  ON_DEVICE(h);
+  CU(cudaEventSynchronize(h->done_ev[slot]));
+  h->slot_ticket[slot] = 0;
+  return WAT_OK;
+}
+
+static int tag_host_impl(wat_handle* h, const void* pcm_host, bool i16, int64_t clip_stride, const int32_t* n_valid,
+                         int32_t n_samples, int32_t B, int32_t dw, float* logits_host) {
+  int64_t ticket = 0;
+  if (int rc = tag_host_submit(h, pcm_host, i16, clip_stride, n_valid, n_samples, B, dw, logits_host, &ticket)) return rc;
+  return tag_host_wait(h, ticket);
 }
 
 int wat_tag(wat_handle* h, const float* pcm, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples, int32_t B,
@@ -964,6 +999,18 @@ int wat_tag_host_pcm16(wat_handle* h, const int16_t* pcm_host, int64_t clip_stri
                        int32_t B, int32_t dw, float* logits_host) {
   return tag_host_impl(h, pcm_host, true, clip_stride, n_valid, n_samples, B, dw, logits_host);
 }
+
+int wat_tag_host_submit(wat_handle* h, const float* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                        int32_t B, int32_t dw, float* logits_host, int64_t* ticket) {
+  if (!ticket) return fail(WAT_ERR_INVALID, "null ticket");
+  return tag_host_submit(h, pcm_host, false, clip_stride, n_valid, n_samples, B, dw, logits_host, ticket);
+}
+int wat_tag_host_submit_pcm16(wat_handle* h, const int16_t* pcm_host, int64_t clip_stride, const int32_t* n_valid, int32_t n_samples,
+                              int32_t B, int32_t dw, float* logits_host, int64_t* ticket) {
+  if (!ticket) return fail(WAT_ERR_INVALID, "null ticket");
+  return tag_host_submit(h, pcm_host, true, clip_stride, n_valid, n_samples, B, dw, logits_host, ticket);
+}
+int wat_tag_host_wait(wat_handle* h, int64_t ticket) { return tag_host_wait(h, ticket); }
 
 int64_t wat_workspace_bytes(const wat_handle* h) { return h ? h->ws_bytes : 0; }
 int64_t wat_kernel_launches(const wat_handle* h) { return h ? h->launches : 0; }

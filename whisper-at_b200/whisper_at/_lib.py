@@ -55,6 +55,9 @@ _SIGS = {
     "wat_tag_host": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp]),
     "wat_tag_pcm16": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp, _vp]),
     "wat_tag_host_pcm16": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp]),
+    "wat_tag_host_submit": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp, _vp]),
+    "wat_tag_host_submit_pcm16": (C.c_int, [_vp, _fp, _i64, _vp, _i32, _i32, _i32, _fp, _vp]),
+    "wat_tag_host_wait": (C.c_int, [_vp, _i64]),
     "wat_workspace_bytes": (_i64, [_vp]),
     "wat_kernel_launches": (_i64, [_vp]),
     "wat_num_sms": (C.c_int, [_vp]),

@@ -152,6 +152,20 @@ class _Engine:
         return int(self.L.wat_kernel_launches(self.h))
 
 
+class PendingTags:
+    """A queued `tag_batch_host_async` call; keeps its host buffers alive until the result has been taken."""
+
+    def __init__(self, eng, ticket: int, audio: Tensor, out: Tensor):
+        self._eng, self._ticket, self._audio, self._out = eng, ticket, audio, out
+
+    def result(self) -> Tensor:
+        if self._eng is not None:
+            with torch.cuda.device(self._eng.device):
+                _lib.check(self._eng.L.wat_tag_host_wait(self._eng.h, self._ticket))
+            self._eng = self._audio = None
+        return self._out
+
+
 class Whisper(nn.Module):
     """model.py:224-318, tagging path only."""
 
@@ -272,9 +286,17 @@ class Whisper(nn.Module):
                        precision: Optional[str] = None, n_valid: Optional[np.ndarray] = None) -> Tensor:
         """Same through HOST buffers (wat_tag_host): `audio` is a CPU tensor [B, n] (pinned for full
         speed); returns CPU logits.  H2D copy, compute and D2H copy all happen inside the call."""
+        return self.tag_batch_host_async(audio, at_time_res, out, precision, n_valid).result()
+
+    def tag_batch_host_async(self, audio: Tensor, at_time_res=10, out: Optional[Tensor] = None,
+                             precision: Optional[str] = None, n_valid: Optional[np.ndarray] = None) -> "PendingTags":
+        """Queue one host-buffer tagging call (wat_tag_host_submit) and return at once; `.result()` waits
+        (wat_tag_host_wait) and returns the CPU logits.  Two calls may be in flight per model: submitting batch t+1
+        before asking for the result of batch t moves its PCM over PCIe while batch t computes.  `audio` and `out`
+        should be pinned and must not be modified until `.result()` returns."""
         eng = self.engine(precision)
         assert audio.ndim == 2 and audio.shape[1] <= 480000 and not audio.is_cuda
-        i16 = audio.dtype == torch.int16                           # 16-bit PCM: half the H2D bytes (wat_tag_host_pcm16)
+        i16 = audio.dtype == torch.int16                           # 16-bit PCM: half the H2D bytes (wat_tag_host_submit_pcm16)
         a = audio.contiguous() if i16 else audio.to(torch.float32).contiguous()
         B, n = a.shape
         dw = int(at_time_res * 2.5)
@@ -287,10 +309,11 @@ class Whisper(nn.Module):
             nv_arr = np.ascontiguousarray(n_valid, dtype=np.int32)
             assert nv_arr.shape == (B,)
             nv = nv_arr.ctypes.data_as(C.c_void_p)
+        ticket = C.c_int64(0)
         with torch.cuda.device(eng.device):
-            fn = eng.L.wat_tag_host_pcm16 if i16 else eng.L.wat_tag_host
-            _lib.check(fn(eng.h, a.data_ptr(), n, nv, n, B, dw, out.data_ptr()))
-        return out
+            fn = eng.L.wat_tag_host_submit_pcm16 if i16 else eng.L.wat_tag_host_submit
+            _lib.check(fn(eng.h, a.data_ptr(), n, nv, n, B, dw, out.data_ptr(), C.byref(ticket)))
+        return PendingTags(eng, ticket.value, a, out)
 
     def kernel_launches(self) -> int:
         return sum(e.launches() for e in self._engines.values())
