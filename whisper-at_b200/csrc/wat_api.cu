@@ -335,16 +335,10 @@ int pack_block_bf16(wat_handle* h, BlockW& b) {
   return 0;
 }
 
-int ensure_ws(wat_handle* h, int B) {
-  const int Bc = B < h->cfg.max_batch ? B : h->cfg.max_batch;
-  if (Bc <= h->ws_B) return 0;
-  const int64_t d = h->d, L = h->L;
-  const int64_t rows_enc = h->head_only ? 0 : (int64_t)Bc * 1500;
-  const int64_t head_rows_clip = L * 150;                         // S*dw < 75 + dw <= 150 for dw <= 75; Tp <= 128 in wat_head_forward
-  int64_t hc = h->head_only ? Bc : rows_enc / head_rows_clip;
-  if (hc < 1) hc = 1;
-  if (hc > Bc) hc = Bc;
-  const int64_t rows_cap = std::max(rows_enc, hc * head_rows_clip);
+// row-proportional part of the workspace: the residual stream and every per-row intermediate of a transformer block
+int ensure_rows(wat_handle* h, int64_t rows_cap, int Bc) {
+  if (rows_cap <= h->rows_cap) return 0;
+  const int64_t d = h->d;
   const size_t es = h->bf16 ? 2 : 4;
   int rc;
   if ((rc = grow(h, h->x, sizeof(float) * rows_cap * d))) return rc;
@@ -359,6 +353,23 @@ int ensure_ws(wat_handle* h, int B) {
     const int64_t np_max = std::max<int64_t>(std::max(d, (int64_t)h->di) / 64, 1);
     if ((rc = grow(h, h->stats, sizeof(float) * 2 * rows_cap * np_max))) return rc;
   }
+  h->rows_cap = rows_cap;
+  return 0;
+}
+
+int ensure_ws(wat_handle* h, int B) {
+  const int Bc = B < h->cfg.max_batch ? B : h->cfg.max_batch;
+  if (Bc <= h->ws_B) return 0;
+  const int64_t d = h->d, L = h->L;
+  const int64_t rows_enc = h->head_only ? 0 : (int64_t)Bc * 1500;
+  const int64_t head_rows_clip = L * 150;                         // S*dw < 75 + dw <= 150 for dw <= 75; Tp <= 128 in wat_head_forward
+  // the encoder's rows, and room for the head rows of at least one clip (a head-only handle: of the whole batch).  run_head
+  // grows this once it knows the decision window, so that the head of a whole batch runs as one chunk (see there).
+  const int64_t rows_cap = std::max(rows_enc, (h->head_only ? (int64_t)Bc : (int64_t)1) * head_rows_clip);
+  const size_t es = h->bf16 ? 2 : 4;
+  int rc;
+  if ((rc = ensure_rows(h, rows_cap, Bc))) return rc;
+  if (!h->head_only && (rc = grow(h, h->hbuf, es * (size_t)Bc * 3000 * 3 * h->cfg.n_mels))) return rc;   // conv1 im2col rows (no-op when rows*4d covers them)
   if (h->bf16 && !h->head_only) {
     if ((rc = grow(h, h->vt, (size_t)2 * Bc * h->H * VT_ROWS * 1536, true))) return rc;   // zeroed: the 36 padding keys stay 0
   }
@@ -369,11 +380,10 @@ int ensure_ws(wat_handle* h, int B) {
     if ((rc = grow(h, h->melT, es * (size_t)Bc * 3000 * h->cfg.n_mels))) return rc;
     if ((rc = grow(h, h->pooled, sizeof(float) * (size_t)Bc * L * 75 * d))) return rc;
   }
-  if ((rc = grow(h, h->lmean, sizeof(float) * (size_t)hc * 75 * d))) return rc;
-  if ((rc = grow(h, h->lnout, sizeof(float) * (size_t)hc * 75 * d))) return rc;
+  if ((rc = grow(h, h->lmean, sizeof(float) * (size_t)Bc * 75 * d))) return rc;
+  if ((rc = grow(h, h->lnout, sizeof(float) * (size_t)Bc * 75 * d))) return rc;
   h->ws_B = Bc;
-  h->rows_cap = rows_cap;
-  h->head_chunk = (int)hc;
+  h->head_chunk = Bc;
   return 0;
 }
 
@@ -529,12 +539,20 @@ int run_head_impl(wat_handle* h, const float* pooled, int B, int t_total, int t_
   const int mode = h->head_mode;
   const bool layerwise = head_has_layer_tr(mode);
   const int64_t rows_clip = (int64_t)S * (layerwise ? L : 1) * dw;
-  int hc = (int)(h->rows_cap / rows_clip);
+  int rc;
+  // One chunk for the whole call when it fits: the head works on S*dw*L rows per clip (1.6x the encoder's 1500 for large-v2 at
+  // 10 s), so the row buffers are grown - once per handle and resolution - up to twice the encoder's size; beyond that the
+  // clips are split into equal chunks.
+  if (!h->head_only) {
+    const int64_t want = (int64_t)std::min(B, h->head_chunk) * rows_clip;
+    const int64_t limit = std::max<int64_t>(h->rows_cap, (int64_t)2 * h->ws_B * 1500);
+    if (want > h->rows_cap && (rc = ensure_rows(h, std::min(want, limit), h->ws_B))) return rc;
+  }
+  int hc = (int)std::min<int64_t>(h->rows_cap / rows_clip, h->head_chunk);
   if (hc < 1) return fail(WAT_ERR_INVALID, "pooled length %d too long for the workspace", t_len);
-  if (hc > h->head_chunk) hc = h->head_chunk;
+  if (hc < B) { const int n_chunks = (B + hc - 1) / hc; hc = (B + n_chunks - 1) / n_chunks; }
   float* x = (float*)h->x.p;
   float* x2 = (float*)h->x2.p;
-  int rc;
   for (int b0 = 0; b0 < B; b0 += hc) {
     const int nb = std::min(hc, B - b0);
     const int rows = (int)(nb * rows_clip);
