@@ -160,24 +160,18 @@ __device__ __forceinline__ void softmax_tile(uint32_t tS, uint32_t tO, uint32_t 
 // Pass 0: P = 2^S with no reference maximum (see the header).  POLY selects which pairs of every 8 scores take the FMA-pipe
 // polynomial instead of MUFU.EX2: bit p of POLY = pair p (scores 2p, 2p+1) of the group; the pattern alternates between the low
 // and the high nibble on odd groups so that e.g. 0x31 gives 1 of 4 and 2 of 4 pairs in turn (37.5%).
-template <bool MASK, bool TRACE, int POLY, int HALVES>
+template <bool MASK, bool TRACE, int POLY>
 __device__ __forceinline__ void softmax_tile_fast(uint32_t tS, uint32_t tP, int nvalid, int j, int n_kv, AttnBars* bars, float& l,
                                                   bool& s_next, long long* tr) {
-  // HALVES = 2: two threads per query row (warps w and w + 4 share a TMEM lane quadrant), each takes 32 of the 64 keys of the
-  // step: tS / tP already point at this thread's columns and nvalid is relative to them.  Without a running maximum the two
-  // threads of a row never talk to each other until the row sums are added at the end of the tile.
-  constexpr int NC = 64 / HALVES;
+  constexpr int NC = AT_KV;
   uint32_t a[NC];
-  if constexpr (HALVES == 1) {
+  {
     uint32_t lo[32], hi[32];
     tmem_ld32(tS, lo);
     tmem_ld32(tS + 32, hi);
     tc_wait_ld();
 #pragma unroll
     for (int i = 0; i < 32; ++i) { a[i] = lo[i]; a[32 + i] = hi[i]; }
-  } else {
-    tmem_ld32(tS, a);
-    tc_wait_ld();
   }
   tc_fence_before();
   mbar_arrive(&bars->s_free);                                     // S is in registers: Q K(j+1)^T may overwrite the buffer
@@ -219,18 +213,17 @@ __device__ __forceinline__ void softmax_tile_fast(uint32_t tS, uint32_t tP, int 
     if (!okp) mbar_wait_spin(&bars->pv_done, (j - 1) & 1);
     tc_fence_after();
   }
-  if constexpr (HALVES == 1) tmem_st32(tP, pk);
-  else tmem_st16(tP, pk);
+  tmem_st32(tP, pk);
   tc_wait_st();
   const float2 t = __fadd2_rn(__fadd2_rn(ls0, ls1), __fadd2_rn(ls2, ls3));
   l += t.x + t.y;
 }
 
-template <bool TRACE, int POLY, int HALVES>
-__global__ void __launch_bounds__(32 + 128 * HALVES, 3)
+template <bool TRACE, int POLY>
+__global__ void __launch_bounds__(160, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVT, __nv_bfloat16* __restrict__ out, int T, int D, int n_head,
-               int q_tiles, float c_log2, int first_pass, int ctrl, long long* __restrict__ trace, unsigned int* __restrict__ n_repeat) {
+               int q_tiles, float c_log2, int first_pass, long long* __restrict__ trace, unsigned int* __restrict__ n_repeat) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -245,11 +238,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = bh % n_head, b = bh / n_head;
   const int n_kv = (T + AT_KV - 1) / AT_KV;
 
-  // the LAST warp is the control warp; warps 0 .. 4 HALVES - 1 are the softmax warps (TMEM lane quadrant = warp % 4, key half =
-  // warp / 4).  (ctrl is kept as a parameter for the launcher's sake; placing the control warp first made no difference.)
-  ctrl = 4 * HALVES;
-  const int first_sm = 0;
-  __shared__ float s_l[128 * HALVES];
+  // warps 0..3 are the softmax warps (TMEM lane quadrant = warp), the LAST warp is the control warp (placing it first made
+  // no difference)
+  constexpr int ctrl = 4, first_sm = 0;
   if (warp == ctrl && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -278,9 +269,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < AT_KSTAGE; ++s) mbar_init(&bars->k_full[s], 1);
     for (int s = 0; s < AT_NSTAGE; ++s) mbar_init(&bars->v_full[s], 1);
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, fast ? 128 * HALVES : 128);          // pass 1 (running max): one thread per row, warps 0..3
+    mbar_init(&bars->p_full, 128);                                 // one arrival per softmax thread (= query row)
     mbar_init(&bars->pv_done, 1);
-    mbar_init(&bars->s_free, fast ? 128 * HALVES : 128);
+    mbar_init(&bars->s_free, 128);
     fence_mbar_init();
     // first loads right away: their latency (the Q tile is always a first touch) overlaps the TMEM allocation and the CTA
     // barrier below; nobody else touches these barriers before that barrier
@@ -383,9 +374,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       AT_TRACE(512, j, 4);
     }
-  } else if (fast || warp < 4) {
-    const int q = warp & 3;
-    const int half = fast ? (warp >> 2) : 0;                      // which 32 keys of every step (two threads per row, pass 0)
+  } else {
+    const int q = warp;
     const int r = q * 32 + lane;                                  // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;                            // reference max (log2 units, may lag by <= 24), row sum
@@ -399,10 +389,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int nvalid = T - j * AT_KV;
       const uint32_t tS = tmem_base + lane_off;
       if (fast) {
-        constexpr int NC = AT_KV / HALVES;
-        const uint32_t tSh = tS + half * NC, tPh = tmem_P + lane_off + half * (NC / 2);
-        if (nvalid >= AT_KV) softmax_tile_fast<false, TRACE, POLY, HALVES>(tSh, tPh, NC, j, n_kv, bars, l, s_ready, tr);
-        else softmax_tile_fast<true, TRACE, POLY, HALVES>(tSh, tPh, nvalid - half * NC, j, n_kv, bars, l, s_ready, tr);
+        if (nvalid >= AT_KV) softmax_tile_fast<false, TRACE, POLY>(tS, tmem_P + lane_off, AT_KV, j, n_kv, bars, l, s_ready, tr);
+        else softmax_tile_fast<true, TRACE, POLY>(tS, tmem_P + lane_off, nvalid, j, n_kv, bars, l, s_ready, tr);
       } else {
         if (nvalid >= AT_KV) softmax_tile<false, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, AT_KV, j, n_kv, bars, m_used, l, s_ready, tr);
         else softmax_tile<true, TRACE>(tS, tmem_O + lane_off, tmem_P + lane_off, c_log2, nvalid, j, n_kv, bars, m_used, l, s_ready, tr);
@@ -414,20 +402,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_wait_spin(&bars->pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    // the row sum of a row whose keys were split over two threads
-    const int n_sm = fast ? 128 * HALVES : 128;                   // softmax threads of this pass
-    if (fast && HALVES == 2) {
-      s_l[half * 128 + r] = l;
-      named_bar_sync(1, n_sm);
-      l = s_l[r] + s_l[128 + r];
-    }
     // pass 0 is accepted iff every row sum stayed inside the exponent range (inf and NaN fail the comparisons too)
     if (fast && !(l >= 7.888609052e-31f && l <= 1.267650600e30f)) s_bad = 1;
-    named_bar_sync(1, n_sm);
+    named_bar_sync(1, 128);                                        // the four softmax warps: s_bad is final
     if (!(fast && s_bad)) {
-      // O / l: with two threads per row each writes 32 of the head's 64 output columns
+      // O / l
       const int tq = qt * 128 + r;
-      const int ncol = (fast && HALVES == 2) ? 32 : 64, c0 = (fast && HALVES == 2) ? half * 32 : 0;
+      constexpr int ncol = 64, c0 = 0;
       __nv_bfloat16* op = out + ((long long)b * T + tq) * D + h * 64 + c0;
       const float inv = 1.0f / l;
 #pragma unroll 1
@@ -471,16 +452,16 @@ static bool make_map_bf16(CUtensorMap* m, const void* ptr, int rank, const cuuin
 }
 
 // POLY patterns of softmax_tile_fast (share of the exponentials evaluated on the FMA pipe): 0x11 = 25%, 0x31 = 37.5%, 0x33 = 50%
-template <int POLY, int HALVES>
+template <int POLY>
 static cudaError_t launch_attn_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, __nv_bfloat16* out, int grid,
                                        int T, int D, int n_head, int q_tiles, float c_log2, int first_pass, long long* trace,
                                        unsigned int* n_repeat, cudaStream_t st) {
   static unsigned long long attr_mask = 0, attr_mask_tr = 0;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false, POLY, HALVES>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
-  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true, POLY, HALVES>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
-  constexpr int threads = 32 + 128 * HALVES;
-  if (trace) attn_tc_kernel<true, POLY, HALVES><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, 0, trace, n_repeat);
-  else attn_tc_kernel<false, POLY, HALVES><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, 0, nullptr, n_repeat);
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<false, POLY>, AT_SMEM, attr_mask); e != cudaSuccess) return e;
+  if (cudaError_t e = opt_in_smem(attn_tc_kernel<true, POLY>, AT_SMEM, attr_mask_tr); e != cudaSuccess) return e;
+  constexpr int threads = 160;
+  if (trace) attn_tc_kernel<true, POLY><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat);
+  else attn_tc_kernel<false, POLY><<<grid, threads, AT_SMEM, st>>>(tmQ, tmK, tmVT, out, T, D, n_head, q_tiles, c_log2, first_pass, nullptr, n_repeat);
   return cudaGetLastError();
 }
 
@@ -516,13 +497,13 @@ cudaError_t launch_attn_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vt, __n
   // One elected mbarrier arrival per softmax warp (barrier counts 4 instead of 128; both arrivals follow a warp-collective
   // tcgen05.wait) was measured too: 81.5-82.3 ms against 78.8-79.0 ms on the same box - the __syncwarp and the divergent
   // branch cost more than the 32 per-thread arrivals they replace.
-  // HALVES = 2 (two threads per query row in the max-free pass, 9 warps per CTA) is implemented above and was measured:
-  // 94 ms per step against 81 ms for one thread per row on the same box - more warps per step cost more in hand-overs and
-  // registers (72 per thread) than the shorter per-thread exponential phase gains.  Only HALVES = 1 is instantiated.
-#define WAT_ATTN_LAUNCH(P, H) launch_attn_variant<P, H>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st)
-  if (poly == 0) return WAT_ATTN_LAUNCH(0x11, 1);
-  if (poly == 2) return WAT_ATTN_LAUNCH(0x33, 1);
-  return WAT_ATTN_LAUNCH(0x31, 1);
+  // Two threads per query row in the max-free pass (9 warps per CTA, each softmax thread 32 of the 64 keys of a step) was built
+  // and measured: 94 ms per step against 81 ms for one thread per row on the same box - more warps per step cost more in
+  // hand-overs and registers (72 per thread) than the shorter per-thread exponential phase gains.  Removed again.
+#define WAT_ATTN_LAUNCH(P) launch_attn_variant<P>(tmQ, tmK, tmVT, out, grid, T, D, n_head, q_tiles, c_log2, first_pass, trace, n_repeat, st)
+  if (poly == 0) return WAT_ATTN_LAUNCH(0x11);
+  if (poly == 2) return WAT_ATTN_LAUNCH(0x33);
+  return WAT_ATTN_LAUNCH(0x31);
 #undef WAT_ATTN_LAUNCH
 }
 

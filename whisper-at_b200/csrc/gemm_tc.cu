@@ -334,14 +334,13 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmTcDev& g, int row, b
 #pragma unroll
     for (int i = 0; i < 32; i += 8) gelu_erf_poly8(v + i);
   }
-  if (false) {
-  } else if (g.epi == TC_EPI_QKV) {
+  if (g.epi == TC_EPI_QKV) {
     const int vc = n0 - 2 * g.D;                         // h * 64 + e ; a 32-chunk never straddles a head
     const int h = vc >> 6, e0 = vc & 63;
     __nv_bfloat16* vp = g.vt + (((long long)vb * g.n_head + h) * VT_ROWS + e0) * g.seq_Tpad + vtok;
 #pragma unroll
     for (int i = 0; i < 32; ++i) vp[(long long)i * g.seq_Tpad] = __float2bfloat16_rn(v[i]);
-  } else {
+  } else {                                                       // fp32 output without a transpose tile (16-epilogue-warp kernel only)
     if (g.epi == TC_EPI_F32_RES) {
       const long long rr = g.r_mod > 0 ? (row % g.r_mod) : row;
       const float* rp = g.R + rr * g.ldr + n0;
