@@ -1,7 +1,16 @@
 #!/bin/bash
+# mel tests + mel time at configs 5 and 2
 mkdir -p gpurun_out
 export PYTHONDONTWRITEBYTECODE=1
-timeout 900 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "mel or tiny_fp32 or transcribe or int16 or smoke" > gpurun_out/pytest_mel.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_mel.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-TAG=r02f CFGS="2 5" bash tools/gpu_cfgs.sh
-bash tools/gpu_ncu_all.sh
+timeout 900 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "mel or int16 or tiny_fp32 or host" > gpurun_out/mel_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/mel_pytest.log
+for c in 5 2; do
+  timeout 900 python bench.py --config $c --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-baseline --long-file-minutes 0 > gpurun_out/mel_cfg$c.json 2> gpurun_out/mel_cfg$c.err; echo "cfg $c exit $?"
+  python - gpurun_out/mel_cfg$c.json <<'PY'
+import json,sys
+try:
+    j=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print('value',round(j['value']),'e2e',round(j['e2e']['value']),'ms/step',round(j['ms_per_step'],2),'mel ms',round(j['kernel_profile']['mel']['ms_per_step'],3), j['clocks'])
+except Exception as e: print('parse fail',e)
+PY
+  tail -3 gpurun_out/mel_cfg$c.err
+done

@@ -21,7 +21,7 @@
 
 namespace wat {
 
-constexpr int MEL_F = 10;                          // frames per CTA
+constexpr int MEL_F = 10;                          // frames per CTA (even: the mel projection splits them in two halves)
 constexpr int MEL_THREADS = 256;
 constexpr int MEL_SPAN = MEL_F * 160 + 240;        // samples a CTA touches
 constexpr int MEL_BINS = 200;                      // bins 0..199 (200 has zero weight)
@@ -76,13 +76,26 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
   const short* xi = reinterpret_cast<const short*>(pcm) + (long long)clip * clip_stride;
 
   const int s0 = t0 * 160 - 200;
-  for (int i = tid; i < MEL_SPAN; i += MEL_THREADS) {
-    int s = s0 + i;
-    if (s < 0) s = -s;                                                    // reflect about sample 0
-    if (s >= n_total) s = 2 * (n_total - 1) - s;                          // reflect about the padded end
-    float smp = 0.f;                                                      // appended `padding` samples are zero
-    if (s >= 0 && s < n_valid) smp = pcm_i16 ? (float)__ldg(xi + s) * (1.0f / 32768.0f) : __ldg(xf + s);
-    xs[i] = smp;
+  {
+    // every load of the thread is issued before the first store (the loop used to wait for each sample in turn: 24% of the
+    // kernel's stall samples sat on that store)
+    constexpr int NLD = (MEL_SPAN + MEL_THREADS - 1) / MEL_THREADS;
+    float v[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = tid + k * MEL_THREADS;
+      int s = s0 + i;
+      if (s < 0) s = -s;                                                  // reflect about sample 0
+      if (s >= n_total) s = 2 * (n_total - 1) - s;                        // reflect about the padded end
+      float smp = 0.f;                                                    // appended `padding` samples are zero
+      if (i < MEL_SPAN && s >= 0 && s < n_valid) smp = pcm_i16 ? (float)__ldg(xi + s) * (1.0f / 32768.0f) : __ldg(xf + s);
+      v[k] = smp;
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = tid + k * MEL_THREADS;
+      if (i < MEL_SPAN) xs[i] = v[k];
+    }
   }
   for (int i = tid; i < 400; i += MEL_THREADS) { const double2 t = twiddle[i]; tw[i] = make_double2(t.x, -t.y); }
   for (int i = tid; i < MEL_F; i += MEL_THREADS) pw[i * MEL_BINS] = 0.f;   // bin 0 is never formed (zero filter weight)
@@ -153,18 +166,30 @@ mel_power_kernel(const void* __restrict__ pcm, int pcm_i16, long long clip_strid
   }
   __syncthreads();
 
+  // mel projection: an item = one filter x one half of the CTA's frames, so a weight is fetched once for MEL_F / 2 frames and
+  // the frames give independent accumulation chains
   float lmax = -INFINITY;
-  for (int i = tid; i < MEL_F * n_mels; i += MEL_THREADS) {
-    const int f = i / n_mels, m = i - f * n_mels;
-    const int t = t0 + f;
-    if (t >= n_frames) continue;
+  constexpr int FH = MEL_F / 2;
+  for (int i = tid; i < 2 * n_mels; i += MEL_THREADS) {
+    const int half = i >= n_mels ? 1 : 0, m = i - half * n_mels;
     const int b0 = fb_start[m], o0 = fb_off[m], cnt = fb_off[m + 1] - o0;
-    const float* p = pw + f * MEL_BINS + b0;
-    float acc = 0.f;
-    for (int j = 0; j < cnt; ++j) acc = fmaf(fb_w[o0 + j], p[j], acc);
-    const float v = log10f(fmaxf(acc, 1e-10f));
-    lmax = fmaxf(lmax, v);
-    if (t < n_store) logspec[((long long)clip * frames_alloc + t) * n_mels + m] = v;
+    const float* p = pw + (half * FH) * MEL_BINS + b0;
+    float acc[FH];
+#pragma unroll
+    for (int f = 0; f < FH; ++f) acc[f] = 0.f;
+    for (int j = 0; j < cnt; ++j) {
+      const float w = fb_w[o0 + j];
+#pragma unroll
+      for (int f = 0; f < FH; ++f) acc[f] = fmaf(w, p[f * MEL_BINS + j], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < FH; ++f) {
+      const int t = t0 + half * FH + f;
+      if (t >= n_frames) continue;
+      const float v = log10f(fmaxf(acc[f], 1e-10f));
+      lmax = fmaxf(lmax, v);
+      if (t < n_store) logspec[((long long)clip * frames_alloc + t) * n_mels + m] = v;
+    }
   }
   lmax = warp_max(lmax);
   if ((tid & 31) == 0) s_max[tid >> 5] = lmax;
