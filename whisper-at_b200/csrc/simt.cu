@@ -422,13 +422,18 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const TIn* __restrict__
 }
 
 // bf16 fast path of the head attention for T <= 32 (decision windows of <= 32 pooled frames; <= 32 encoder layers) and
-// hd % 16 == 0.  One CTA per (sequence, head):
-//   1. S = Q K^T on mma.sync m16n8k16 (bf16 in, fp32 accumulate; a 32x32 padded tile, the contraction split over the 8
-//      warps, fragments loaded straight from global memory - every Q / K element is used exactly once), partial tiles
-//      summed through smem in a fixed order;
-//   2. row softmax in fp32 (warp per row);
-//   3. O = P V in fp32 FMAs: thread = 4 columns x 16 rows, V read once per row half, P broadcast from smem.
-// (The tcgen05 path is reserved for the encoder: these tiles are 25x25 and the whole head attention is ~2% of a step.)
+// hd % 16 == 0.  One CTA per (GROUP of sequences, head): G = 32 / T consecutive sequences (their rows are contiguous) share one
+// 32 x 32 score tile, whose off-diagonal blocks are masked - at at_time_res = 2 (T = 5) that is 6 sequences per CTA instead
+// of a 97%-empty tile each.
+//   1. S = Q K^T on mma.sync m16n8k16 (bf16 in, fp32 accumulate; the contraction split over the 8 warps, fragments loaded
+//      straight from global memory - every Q / K element is used exactly once), partial tiles summed through smem in a
+//      fixed order;
+//   2. row softmax in fp32 over the row's own sequence (warp per row);
+//   3. O = P V in fp32 FMAs: thread = 4 columns x 16 rows, V read once per row half, P broadcast from smem (zero outside
+//      the row's sequence).
+// Per-sequence results do not depend on G or on the sequence's position in its group: the masked terms are exact zeros and
+// every row sums its own keys in the same order.
+// (The tcgen05 path is reserved for the encoder: these tiles are at most 32 x 32 and the whole head attention is ~1% of a step.)
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -436,13 +441,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// PACK = false: one sequence per CTA (T > 16), every bound is T itself
+template <bool PACK>
 __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                              __nv_bfloat16* __restrict__ out, int T, int n_head, int hd,
-                                                             float scale2) {
+                                                             float scale2, int n_seq, int G) {
   __shared__ float Sp[8][32][33];                         // per-warp partial scores; Sp[0] is reused for P
-  const int seq = blockIdx.x, h = blockIdx.y;
+  const int seq0 = PACK ? blockIdx.x * G : blockIdx.x, h = blockIdx.y;
+  const int R = PACK ? min(G, n_seq - seq0) * T : T;       // rows (= keys) of this tile
   const int D = n_head * hd;
-  const long long row0 = (long long)seq * T;
+  const long long row0 = (long long)seq0 * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
   const __nv_bfloat16* qb = qkv + row0 * 3 * D + h * hd;
@@ -465,17 +473,17 @@ __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16
         const int r0 = mt * 16 + g, r1 = r0 + 8;
         const uint32_t* p0 = reinterpret_cast<const uint32_t*>(qb + (long long)r0 * 3 * D + k0);
         const uint32_t* p1 = reinterpret_cast<const uint32_t*>(qb + (long long)r1 * 3 * D + k0);
-        a[mt][0] = r0 < T ? p0[0] : 0u;
-        a[mt][1] = r1 < T ? p1[0] : 0u;
-        a[mt][2] = r0 < T ? p0[4] : 0u;                   // columns + 8
-        a[mt][3] = r1 < T ? p1[4] : 0u;
+        a[mt][0] = r0 < R ? p0[0] : 0u;
+        a[mt][1] = r1 < R ? p1[0] : 0u;
+        a[mt][2] = r0 < R ? p0[4] : 0u;                   // columns + 8
+        a[mt][3] = r1 < R ? p1[4] : 0u;
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int n = nt * 8 + g;
         const uint32_t* pk = reinterpret_cast<const uint32_t*>(kb + (long long)n * 3 * D + k0);
-        b[nt][0] = n < T ? pk[0] : 0u;
-        b[nt][1] = n < T ? pk[4] : 0u;
+        b[nt][0] = n < R ? pk[0] : 0u;
+        b[nt][1] = n < R ? pk[4] : 0u;
       }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -494,29 +502,33 @@ __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16
       }
   }
   __syncthreads();
-  for (int i = warp; i < T; i += 8) {                     // row i is only ever touched by this warp from here on
+  for (int i = warp; i < R; i += 8) {                     // row i is only ever touched by this warp from here on
+    const int j0 = PACK ? (i / T) * T : 0;                 // keys of row i's own sequence: [j0, j0 + T)
+    const bool mine = lane >= j0 && lane < j0 + T;
     float sc = -INFINITY;
-    if (lane < T) {
+    if (mine) {
       float a = Sp[0][i][lane];
 #pragma unroll
       for (int k = 1; k < 8; ++k) a += Sp[k][i][lane];
       sc = a * scale2;
     }
     const float mx = warp_max(sc);
-    const float p = lane < T ? expf(sc - mx) : 0.f;
+    const float p = mine ? expf(sc - mx) : 0.f;
     const float inv = 1.0f / warp_sum(p);
-    Sp[0][i][lane] = p * inv;
+    Sp[0][i][lane] = p * inv;                              // exact zeros outside the sequence (and for lanes >= R)
   }
   __syncthreads();
-  const int ncg = hd >> 2, halves = (T + 15) >> 4;
+  const int ncg = hd >> 2, halves = (R + 15) >> 4;
   for (int idx = threadIdx.x; idx < ncg * halves; idx += 256) {
     const int half = idx / ncg, e = (idx - half * ncg) * 4;
     const int rbase = half * 16;
+    // keys that any of the 16 rows of this half can see: the sequences overlapping [rbase, rbase + 16)
+    const int jlo = PACK ? (rbase / T) * T : 0, jhi = PACK ? min(R, ((min(rbase + 15, R - 1)) / T + 1) * T) : T;
     float4 acc[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 5
-    for (int j = 0; j < T; ++j) {
+    for (int j = jlo; j < jhi; ++j) {
       const float4 v4 = load4(vb + (long long)j * 3 * D + e);
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
@@ -527,7 +539,7 @@ __global__ void __launch_bounds__(256) attn_small_mma_kernel(const __nv_bfloat16
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r)
-      if (rbase + r < T) store4<__nv_bfloat16>(out + (row0 + rbase + r) * D + h * hd + e, acc[r]);
+      if (rbase + r < R) store4<__nv_bfloat16>(out + (row0 + rbase + r) * D + h * hd + e, acc[r]);
   }
 }
 
@@ -544,7 +556,10 @@ cudaError_t launch_attn_small(const void* qkv, bool in_bf16, void* out, bool out
     if (cudaError_t e = opt_in_smem(attn_small_kernel<__nv_bfloat16, __nv_bfloat16>, 80 * 1024, attr_mask_h); e != cudaSuccess) return e;
   }
   if (in_bf16 && out_bf16 && T <= 32 && (hd & 15) == 0) {
-    attn_small_mma_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2);
+    const int G = 32 / T;                                  // sequences per 32 x 32 score tile
+    dim3 grid_g((n_seq + G - 1) / G, n_head);
+    if (G > 1) attn_small_mma_kernel<true><<<grid_g, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2, n_seq, G);
+    else attn_small_mma_kernel<false><<<grid_g, 256, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, T, n_head, hd, scale2, n_seq, 1);
     return cudaGetLastError();
   }
   if (!in_bf16 && !out_bf16)
