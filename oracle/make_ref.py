@@ -23,15 +23,24 @@ DST_ROOT = os.path.join(ROOT, "oracle", "_ref")
 DST = os.path.join(DST_ROOT, "whisper_at")
 
 
+def _make_writable(root: str) -> None:
+    for base, dirs, files in os.walk(root):
+        os.chmod(base, 0o755)
+        for f in files:
+            os.chmod(os.path.join(base, f), 0o644)
+
+
 def make_ref(verbose: bool = True) -> bool:
     if not os.path.isdir(SRC):
         if verbose:
             print(f"make_ref: {SRC} not present; keeping whatever is in {DST_ROOT}")
         return os.path.isdir(DST)
     if os.path.isdir(DST):
+        _make_writable(DST)
         shutil.rmtree(DST)
     os.makedirs(DST_ROOT, exist_ok=True)
-    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"), copy_function=shutil.copyfile)
+    _make_writable(DST)                                  # the source tree is read-only; the copy must stay replaceable
     prov = {}
     for base, _, files in os.walk(DST):
         for f in sorted(files):
