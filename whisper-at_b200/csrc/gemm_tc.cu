@@ -41,6 +41,7 @@ struct GemmTcDev {
   const float* R; long long ldr; int r_mod;
   int M, N, K, act, epi;
   int tma_store;           // bf16 outputs leave through smem + TMA store (CTA-pair kernel)
+  int res_tma;             // residual epilogue in row layout: residual box in by TMA load, x (fp16) and xb (bf16) boxes out by TMA store
   __nv_bfloat16* vt; int seq_T; int seq_Tpad; int n_head; int D;
   float q_scale;           // QKV epilogue: q columns [0, D) are multiplied by it (0 = off)
   int c_f16, r_f16;        // fp32 epilogues: C is stored / R is read as fp16 (the bf16 mode's residual stream)
@@ -395,6 +396,69 @@ __device__ __forceinline__ void tc_epilogue_chunk_bf16_tma(const GemmTcDev& g, c
   }
 }
 
+// Residual epilogue in ROW layout (CTA-pair kernel, fp16 residual stream): thread = output row from the TMEM load to the end.
+// The chunk's 32 x 32 fp16 residual box arrives by a TMA load issued TWO chunks earlier (three warp-private boxes and
+// mbarriers in turn), the sum acc + bias + residual is formed in fp32, its (sum, sum of squares) stay in the thread's registers
+// (a row's statistics need no other lane), the fp16 row goes back into the residual's own box, the bf16 copy into a fourth
+// box, and each box leaves by ONE TMA store.  Against the transposing epilogue above this drops the fp32 transpose through
+// smem, the per-lane statistics slots and every per-row address and predicate (the tensor maps clip rows >= M): ~180 instead
+// of ~500 instructions per chunk.
+// Hand-over of the boxes: the only wait on the bulk stores sits AFTER the chunk's arithmetic, where the previous chunk's boxes
+// have long been read out; it frees the bf16 box for this chunk and box (cc + 2) % 3 = (cc - 1) % 3 for the load of chunk
+// cc + 2, which is issued right behind this chunk's stores - a full chunk ahead of its use.
+// `wst`: 8 KB = residual boxes 0..2 | bf16 box (2 KB each, 64-byte-swizzled like the bf16 store box); `rbar`: 3 mbarriers.
+__device__ __forceinline__ void tc_epilogue_chunk_res_tma(const CUtensorMap* tmX, const CUtensorMap* tmXB, const CUtensorMap* tmR,
+                                                          uint8_t* wst, uint64_t* rbar, uint32_t cc, int row_base, int n0,
+                                                          const uint32_t (&r)[32], const float* bias_chunk, int lane, int nxt_row_base,
+                                                          int nxt_n0, float2& st) {
+  const uint32_t bi = cc % 3;
+  uint8_t* rin = wst + bi * 2048;
+  uint8_t* xbb = wst + 3 * 2048;
+  mbar_wait(&rbar[bi], (cc / 3) & 1);                             // this chunk's residual box has landed
+  const int sw = (lane >> 1) & 3;
+  uint8_t* my = rin + lane * 64;
+  uint4 xbo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint8_t* slot = my + ((c ^ sw) << 4);
+    const uint4 rv = *reinterpret_cast<const uint4*>(slot);       // 8 halves of this row
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[c * 8 + e]);
+    if (bias_chunk) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_chunk + c * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_chunk + c * 8 + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    const float4 r0 = f16x4_to_f32(rv.x, rv.y), r1 = f16x4_to_f32(rv.z, rv.w);
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    st.x += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    st.y = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], fmaf(v[4], v[4], fmaf(v[5], v[5], fmaf(v[6], v[6], fmaf(v[7], v[7], st.y))))))));
+    // a lane only ever touches its own row of a box: the fp16 result overwrites the residual it was read from
+    *reinterpret_cast<uint4*>(slot) = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+    xbo[c] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  if (lane == 0) tma_store_wait_read();                           // chunk cc - 1's boxes (its x box, the bf16 box) have left smem
+  __syncwarp();
+  uint8_t* myb = xbb + lane * 64;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(myb + ((c ^ sw) << 4)) = xbo[c];
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmX, rin, n0, row_base);
+    tma_store_2d(tmXB, xbb, n0, row_base);
+    tma_store_commit();
+    if (nxt_row_base >= 0) {                                      // the residual box of chunk cc + 2
+      const uint32_t nb = (cc + 2) % 3;
+      mbar_expect_tx(&rbar[nb], 2048);
+      tma_load_2d(wst + nb * 2048, tmR, &rbar[nb], nxt_n0, nxt_row_base);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcDev g) {
@@ -552,13 +616,15 @@ template <int EW, int STAGES> struct Tc2Cfg {
   static constexpr int WARP_STAGE_BYTES = F32_STAGE ? 7168 : 2048;   // (+ 32 x 8 float2 row-statistics slots)
   static constexpr int STAGE_AREA = EW * WARP_STAGE_BYTES;
   static constexpr int BIAS_AREA = 2 * EW * COLS * 4;            // this warp's bias slice of the current tile + its LN column sums
-  static constexpr int SMEM_BYTES = STAGES * TC2_STAGE_BYTES + 1024 + STAGE_AREA + BIAS_AREA + 256;
+  // res_tma epilogue (8 warps): the stage and bias areas together are 8 x 8 KB = four 2 KB boxes per warp; its 8 x 3 mbarriers follow
+  // the pipeline barriers
+  static constexpr int SMEM_BYTES = STAGES * TC2_STAGE_BYTES + 1024 + STAGE_AREA + BIAS_AREA + 384;
 };
 
 template <int EW, int TC2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<EW, TC2_STAGES>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                const GemmTcDev g) {
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmXB, const GemmTcDev g) {
   constexpr int BN = 256;
   using Cfg2 = Tc2Cfg<EW, TC2_STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -593,6 +659,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+  const bool res_tma = EW == 8 && g.res_tma != 0;
+  static_assert(EW != 8 || Cfg2::STAGE_AREA + Cfg2::BIAS_AREA == 8 * 8192, "res_tma: four 2 KB boxes per epilogue warp");
+  uint64_t* res_bars = bars + 16;                                  // 8 warps x 3 (res_tma only)
+  if (res_tma && warp >= 2 && lane == 0) {                         // warp-private barriers of the residual boxes (tc_epilogue_chunk_res_tma)
+    uint64_t* rbar = res_bars + (warp - 2) * 3;
+    mbar_init(&rbar[0], 1);
+    mbar_init(&rbar[1], 1);
+    mbar_init(&rbar[2], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmXB);
+    tma_prefetch_desc(&tmC);
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -682,8 +761,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int COLS = Cfg2::COLS;
     int it = 0;
     // fp32 residual epilogue (8 warps): the residual block of a chunk is loaded one chunk (or one tile) ahead of its use
-    const bool res_ahead = EW == 8 && g.epi == TC_EPI_F32_RES;
+    const bool res_ahead = EW == 8 && g.epi == TC_EPI_F32_RES && !res_tma;
     float4 res[8];
+    uint8_t* wst = epi_stage_area + (warp - 2) * 8192;            // res_tma: this warp's four boxes (spans the stage and bias areas)
+    uint64_t* rbar = res_bars + (warp - 2) * 3;
+    uint32_t cc = 0;                                               // chunks this warp has processed (residual box / barrier phase)
+    // coordinates of this warp's k-th chunk (4 chunks per tile, tiles cluster_id, cluster_id + n_clusters, ...); false past the end
+    auto chunk_at = [&](int k, int& rb, int& cn0) {
+      const int t = cluster_id + (k >> 2) * n_clusters;
+      if (t >= total_tiles) return false;
+      rb = (t / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
+      cn0 = (t % n_tiles) * BN + chalf * COLS + (k & 3) * 32;
+      return true;
+    };
+    if (res_tma && lane == 0) {
+      for (int k = 0; k < 2; ++k) {
+        int rb, cn0;
+        if (chunk_at(k, rb, cn0)) { mbar_expect_tx(&rbar[k], 2048); tma_load_2d(wst + k * 2048, &tmR, &rbar[k], cn0, rb); }
+      }
+    }
     if (res_ahead && cluster_id < total_tiles)
       load_residual_chunk(g, (cluster_id / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32, (cluster_id % n_tiles) * BN + chalf * COLS, lane, res);
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
@@ -694,7 +790,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float* my_stage = reinterpret_cast<float*>(epi_stage_area + (warp - 2) * Cfg2::WARP_STAGE_BYTES);
       float* bias_s = epi_bias_area + (warp - 2) * 2 * COLS;
       float* cs_s = bias_s + COLS;
-      if (lane * 4 < COLS) {
+      if (!res_tma && lane * 4 < COLS) {                           // (res_tma reads its bias from global: the area holds its boxes)
         const int nb = n_blk * BN + chalf * COLS + lane * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = b4;
         if (g.bias && nb < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb));
@@ -702,7 +798,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         *reinterpret_cast<float4*>(bias_s + lane * 4) = b4;
         *reinterpret_cast<float4*>(cs_s + lane * 4) = c4;
       }
-      float2* rowacc = (Cfg2::F32_STAGE && g.stats) ? reinterpret_cast<float2*>(my_stage + 32 * 36) : nullptr;
+      float2* rowacc = (Cfg2::F32_STAGE && g.stats && !res_tma) ? reinterpret_cast<float2*>(my_stage + 32 * 36) : nullptr;
+      float2 st_row = make_float2(0.f, 0.f);                      // res_tma: this thread's row, this warp's column slice
       if (rowacc) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) rowacc[k * 32 + lane] = make_float2(0.f, 0.f);
@@ -734,7 +831,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (tr2) tr2[3] = clock64();
         const float* bias_chunk = g.bias ? bias_s + (c0 - chalf * COLS) : nullptr;
         if (g.ln_stats && n_blk * BN + c0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, cs_s + (c0 - chalf * COLS), bias_chunk); bias_chunk = nullptr; }
-        if (res_ahead) {
+        if (res_ahead || res_tma) {
           int nrb = -1, nn0 = 0;
           if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
           else if (tile + n_clusters < total_tiles) {
@@ -742,7 +839,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             nrb = (nt / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
             nn0 = (nt % n_tiles) * BN + chalf * COLS;
           }
-          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, my_stage, lane, tr2, &res, nrb, nn0, rowacc);
+          if (res_tma) {
+            int rb2 = -1, n02 = 0;
+            if (!chunk_at((int)cc + 2, rb2, n02)) rb2 = -1;
+            tc_epilogue_chunk_res_tma(&tmC, &tmXB, &tmR, wst, rbar, cc, row - lane, n_blk * BN + c0, r,
+                                      g.bias ? g.bias + n_blk * BN + c0 : nullptr, lane, rb2, n02, st_row);
+            ++cc;
+          } else {
+            tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, my_stage, lane, tr2, &res, nrb, nn0, rowacc);
+          }
         } else if (g.tma_store && (g.epi == TC_EPI_BF16 || n_blk * BN + c0 < 2 * g.D)) {
           tc_epilogue_chunk_bf16_tma(g, &tmC, row - lane, n_blk * BN + c0, r, bias_chunk, reinterpret_cast<uint8_t*>(my_stage), lane);
         } else {
@@ -750,6 +855,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (tr) tr[2 + (c0 - chalf * COLS) / 32] = clock64();
       }
+      if (res_tma && row_ok) reinterpret_cast<float2*>(g.stats)[(long long)row * g.stats_np + n_blk * (BN / COLS) + chalf] = st_row;
       if (rowacc) {                                               // this warp's slice of the row statistics: partial p = n_blk (BN / COLS) + chalf
         __syncwarp();
         if (row_ok && n_blk * BN + chalf * COLS < g.N) {
@@ -762,7 +868,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
-  if (g.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();     // bulk stores read this CTA's smem: drain before exit
+  if ((g.tma_store || res_tma) && warp >= 2 && lane == 0) tma_store_wait_all();     // bulk stores read this CTA's smem: drain before exit
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
@@ -794,16 +900,27 @@ static bool make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// bf16 output [rows, cols] with row stride ld: box = 32 cols x 32 rows, 64-byte swizzle (the epilogue's TMA store)
-static bool make_map_store(CUtensorMap* m, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+// 16-bit [rows, cols] with row stride ld (elements): box = 32 cols x 32 rows, 64-byte swizzle (the epilogues' TMA stores and the
+// residual box load; rows >= `rows` are clipped on store and zero-filled on load)
+static bool make_map_store(CUtensorMap* m, void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, bool f16 = false) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int res_tma_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("WAT_GEMM_RES_TMA");
+    mode = e ? (atoi(e) != 0) : 1;
+  }
+  return mode;
 }
 
 static int tma_store_mode() {
@@ -825,7 +942,7 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, BN)) return cudaErrorInvalidValue;
   GemmTcDev d;
   d.bias = g.bias; d.C = g.C; d.ldc = g.ldc; d.R = g.R; d.ldr = g.ldr; d.r_mod = g.r_mod;
-  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi; d.tma_store = 0;
+  d.M = g.M; d.N = g.N; d.K = g.K; d.act = g.act; d.epi = g.epi; d.tma_store = 0; d.res_tma = 0;
   d.vt = g.vt; d.seq_T = g.seq_T; d.seq_Tpad = g.seq_Tpad; d.n_head = g.n_head; d.D = g.N / 3; d.q_scale = g.q_scale; d.c_f16 = g.c_f16; d.r_f16 = g.r_f16;
   d.trace = nullptr;
   d.xb = g.xb; d.ldxb = g.ldxb; d.stats = g.stats; d.stats_np = g.stats_np;
@@ -861,10 +978,21 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
     if (!make_map_store(&tmC, g.C, g.M, c_cols, g.ldc)) return cudaErrorInvalidValue;
     d.tma_store = 1;
   }
+  // fp16 residual update that also produces the next LayerNorm's inputs (out-proj, fc2): row-layout epilogue through TMA boxes
+  CUtensorMap tmR = tmA, tmXB = tmA;
+  d.res_tma = 0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (EW == 8 && res_tma_mode() && g.epi == TC_EPI_F32_RES && g.c_f16 && g.r_f16 && g.R && g.xb && g.stats && g.r_mod == 0 && !g.ln_stats &&
+      (g.ldc & 7) == 0 && (g.ldr & 7) == 0 && (g.ldxb & 7) == 0 && al16(g.C) && al16(g.R) && al16(g.xb)) {
+    if (!make_map_store(&tmC, g.C, g.M, g.N, g.ldc, true)) return cudaErrorInvalidValue;
+    if (!make_map_store(&tmR, const_cast<float*>(g.R), g.M, g.N, g.ldr, true)) return cudaErrorInvalidValue;
+    if (!make_map_store(&tmXB, g.xb, g.M, g.N, g.ldxb, false)) return cudaErrorInvalidValue;
+    d.res_tma = 1;
+  }
   const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   int clusters = num_sms / 2;
   if (clusters > total) clusters = total;
-  gemm_tc2_kernel<EW, STAGES><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, d);
+  gemm_tc2_kernel<EW, STAGES><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmR, tmXB, d);
   return cudaGetLastError();
 }
 
