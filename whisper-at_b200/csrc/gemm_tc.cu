@@ -414,21 +414,24 @@ __device__ __forceinline__ void tc_epilogue_chunk_res_tma(const CUtensorMap* tmX
   const uint32_t bi = cc % 3;
   uint8_t* rin = wst + bi * 2048;
   uint8_t* xbb = wst + 3 * 2048;
+  float4 bv[8];                                                   // the chunk's 32 bias values (L1): requested before the box is waited for
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bv[i] = bias_chunk ? __ldg(reinterpret_cast<const float4*>(bias_chunk) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   mbar_wait(&rbar[bi], (cc / 3) & 1);                             // this chunk's residual box has landed
   const int sw = (lane >> 1) & 3;
   uint8_t* my = rin + lane * 64;
   uint4 xbo[4];
+  uint4 rv4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) rv4[c] = *reinterpret_cast<const uint4*>(my + ((c ^ sw) << 4));   // the row's 32 halves, all loads in flight
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint8_t* slot = my + ((c ^ sw) << 4);
-    const uint4 rv = *reinterpret_cast<const uint4*>(slot);       // 8 halves of this row
-    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    const uint32_t rw[4] = {rv4[c].x, rv4[c].y, rv4[c].z, rv4[c].w};
     float2 v[4];                                                  // packed fp32 pairs: FADD2 / FFMA2 halve the instruction count
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = make_float2(__uint_as_float(r[c * 8 + 2 * k]), __uint_as_float(r[c * 8 + 2 * k + 1]));
-    if (bias_chunk) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_chunk + c * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_chunk + c * 8 + 4));
+    {
+      const float4 b0 = bv[2 * c], b1 = bv[2 * c + 1];
       v[0] = __fadd2_rn(v[0], make_float2(b0.x, b0.y)); v[1] = __fadd2_rn(v[1], make_float2(b0.z, b0.w));
       v[2] = __fadd2_rn(v[2], make_float2(b1.x, b1.y)); v[3] = __fadd2_rn(v[3], make_float2(b1.z, b1.w));
     }
@@ -442,7 +445,7 @@ __device__ __forceinline__ void tc_epilogue_chunk_res_tma(const CUtensorMap* tmX
       xb2[k] = pack_bf16(v[k].x, v[k].y);
     }
     // a lane only ever touches its own row of a box: the fp16 result overwrites the residual it was read from
-    *reinterpret_cast<uint4*>(slot) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+    *reinterpret_cast<uint4*>(my + ((c ^ sw) << 4)) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
     xbo[c] = make_uint4(xb2[0], xb2[1], xb2[2], xb2[3]);
   }
   if (lane == 0) tma_store_wait_read();                           // chunk cc - 1's boxes (its x box, the bf16 box) have left smem
@@ -804,6 +807,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         *reinterpret_cast<float4*>(cs_s + lane * 4) = c4;
       }
       float2* rowacc = (Cfg2::F32_STAGE && g.stats && !res_tma) ? reinterpret_cast<float2*>(my_stage + 32 * 36) : nullptr;
+      int nxt_tile_rb = -1, nxt_tile_n0 = 0;                      // res_tma: first chunk of this warp's next tile
+      if (res_tma && tile + n_clusters < total_tiles) {
+        const int nt = tile + n_clusters, nm = nt / n_tiles;
+        nxt_tile_rb = nm * 2 * TC_BM + (int)rank * TC_BM + q * 32;
+        nxt_tile_n0 = (nt - nm * n_tiles) * BN + chalf * COLS;
+      }
       float2 st_s2 = make_float2(0.f, 0.f), st_q2 = st_s2;        // res_tma: (sum, sum of squares) of this thread's row over this warp's column slice, as even / odd column partials
       if (rowacc) {
 #pragma unroll
@@ -838,15 +847,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (g.ln_stats && n_blk * BN + c0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, cs_s + (c0 - chalf * COLS), bias_chunk); bias_chunk = nullptr; }
         if (res_ahead || res_tma) {
           int nrb = -1, nn0 = 0;
-          if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
+          if (res_tma) {}
+          else if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
           else if (tile + n_clusters < total_tiles) {
             const int nt = tile + n_clusters;
             nrb = (nt / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
             nn0 = (nt % n_tiles) * BN + chalf * COLS;
           }
           if (res_tma) {
+            // the chunk two ahead: same tile for the first two chunks, else the next tile's first two (nrb / nn0 above are that
+            // tile's first chunk - one division per tile, not per chunk)
             int rb2 = -1, n02 = 0;
-            if (!chunk_at((int)cc + 2, rb2, n02)) rb2 = -1;
+            const int kc = (c0 - chalf * COLS) >> 5;
+            if (kc < 2) { rb2 = row - lane; n02 = n_blk * BN + c0 + 64; }
+            else if (nxt_tile_rb >= 0) { rb2 = nxt_tile_rb; n02 = nxt_tile_n0 + (kc - 2) * 32; }
             tc_epilogue_chunk_res_tma(&tmC, &tmXB, &tmR, wst, rbar, cc, row - lane, n_blk * BN + c0, r,
                                       g.bias ? g.bias + n_blk * BN + c0 : nullptr, lane, rb2, n02, st_s2, st_q2);
             ++cc;

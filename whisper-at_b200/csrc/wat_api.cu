@@ -1163,7 +1163,18 @@ int wat_dbg_ln_gemm(const void* A1, const void* W1, const float* bias1, const vo
   g.c_f16 = g.r_f16 = x_f16 ? 1 : 0;                              // R and x in fp16: the bf16 mode's residual stream
   g.M = M; g.N = D; g.K = K1; g.epi = TC_EPI_F32_RES; g.force_pair = pair;
   g.xb = (__nv_bfloat16*)xb; g.ldxb = D; g.stats = stats; g.stats_np = gemm_tc_stats_slices(M, D, K1, TC_EPI_F32_RES, pair);
+  long long* trace = nullptr;                                     // WAT_DBG_TRACE=1: clock trace of the producer GEMM's first epilogue warp -> stderr
+  if (getenv("WAT_DBG_TRACE") && pair == 1) { CU(cudaMalloc(&trace, 32 * 8 * 8)); CU(cudaMemsetAsync(trace, 0, 32 * 8 * 8, st)); g.trace = trace; }
   if (e == cudaSuccess) e = launch_gemm_tc(g, sms, st);
+  if (trace) {
+    long long ht[32 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(ht, trace, sizeof(ht), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    for (int i = 0; i < 24; ++i)
+      fprintf(stderr, "tile %2d: start %8lld  wait_mma %6lld  chunks %6lld %6lld %6lld %6lld\n", i, ht[i * 8] - ht[0], ht[i * 8 + 1] - ht[i * 8],
+              ht[i * 8 + 2] - ht[i * 8 + 1], ht[i * 8 + 3] - ht[i * 8 + 2], ht[i * 8 + 4] - ht[i * 8 + 3], ht[i * 8 + 5] - ht[i * 8 + 4]);
+  }
   if (e == cudaSuccess && pooled) e = launch_pool20_bf16((const __nv_bfloat16*)xb, M / 1500, 1500, D, 0, 1, pooled, st);
   GemmTc c;
   memset(&c, 0, sizeof(c));
