@@ -629,7 +629,9 @@ template <int EW, int STAGES> struct Tc2Cfg {
   static constexpr int SMEM_BYTES = STAGES * TC2_STAGE_BYTES + 1024 + STAGE_AREA + BIAS_AREA + 384;
 };
 
-template <int EW, int TC2_STAGES>
+// RES_TMA: the instantiation for the TMA-box residual epilogue (8 epilogue warps); every other epilogue is compiled out of it, and it
+// out of theirs - sharing one kernel cost the QKV epilogue 10% through register spills.
+template <int EW, int TC2_STAGES, bool RES_TMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<EW, TC2_STAGES>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmXB, const GemmTcDev g) {
@@ -667,8 +669,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
-  const bool res_tma = EW == 8 && g.res_tma != 0;
-  static_assert(EW != 8 || Cfg2::STAGE_AREA + Cfg2::BIAS_AREA == 8 * 8192, "res_tma: four 2 KB boxes per epilogue warp");
+  constexpr bool res_tma = RES_TMA;
+  static_assert(!RES_TMA || (EW == 8 && Cfg2::STAGE_AREA + Cfg2::BIAS_AREA == 8 * 8192), "res_tma: 8 epilogue warps, four 2 KB boxes each");
   uint64_t* res_bars = bars + 16;                                  // 8 warps x 3 (res_tma only)
   if (res_tma && warp >= 2 && lane == 0) {                         // warp-private barriers of the residual boxes (tc_epilogue_chunk_res_tma)
     uint64_t* rbar = res_bars + (warp - 2) * 3;
@@ -769,7 +771,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int COLS = Cfg2::COLS;
     int it = 0;
     // fp32 residual epilogue (8 warps): the residual block of a chunk is loaded one chunk (or one tile) ahead of its use
-    const bool res_ahead = EW == 8 && g.epi == TC_EPI_F32_RES && !res_tma;
+    const bool res_ahead = !RES_TMA && EW == 8 && g.epi == TC_EPI_F32_RES;
     float4 res[8];
     uint8_t* wst = epi_stage_area + (warp - 2) * 8192;            // res_tma: this warp's four boxes (spans the stage and bias areas)
     uint64_t* rbar = res_bars + (warp - 2) * 3;
@@ -822,7 +824,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row = m_pair * 2 * TC_BM + (int)rank * TC_BM + q * 32 + lane;
       const bool row_ok = row < g.M;
       float ln_mean = 0.f, ln_rstd = 0.f;
-      if (g.ln_stats) ln_row_scalars(g, row, row_ok, ln_mean, ln_rstd);        // while the tile's MMAs are still running
+      if (!RES_TMA && g.ln_stats) ln_row_scalars(g, row, row_ok, ln_mean, ln_rstd);        // while the tile's MMAs are still running
       long long* tr = (g.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 24) ? g.trace + it * 8 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait(&tmem_full[as], aphase);
@@ -830,7 +832,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (tr) tr[1] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       int vb = 0, vtok = 0;
-      if (g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
+      if (!RES_TMA && g.epi == TC_EPI_QKV && row_ok) { vb = row / g.seq_T; vtok = row - vb * g.seq_T; }
 #pragma unroll 1
       for (int c0 = chalf * COLS; c0 < (chalf + 1) * COLS; c0 += 32) {
         uint32_t r[32];
@@ -844,29 +846,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         long long* tr2 = (tr && c0 == chalf * COLS + 32 && it >= 8 && it < 16) ? g.trace + 24 * 8 + (it - 8) * 4 : nullptr;
         if (tr2) tr2[3] = clock64();
         const float* bias_chunk = g.bias ? bias_s + (c0 - chalf * COLS) : nullptr;
-        if (g.ln_stats && n_blk * BN + c0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, cs_s + (c0 - chalf * COLS), bias_chunk); bias_chunk = nullptr; }
-        if (res_ahead || res_tma) {
+        if (!RES_TMA && g.ln_stats && n_blk * BN + c0 < g.N) { ln_fold_chunk(r, ln_mean, ln_rstd, cs_s + (c0 - chalf * COLS), bias_chunk); bias_chunk = nullptr; }
+        if constexpr (RES_TMA) {
+          // the chunk two ahead: same tile for the first two chunks, else the next tile's first two
+          int rb2 = -1, n02 = 0;
+          const int kc = (c0 - chalf * COLS) >> 5;
+          if (kc < 2) { rb2 = row - lane; n02 = n_blk * BN + c0 + 64; }
+          else if (nxt_tile_rb >= 0) { rb2 = nxt_tile_rb; n02 = nxt_tile_n0 + (kc - 2) * 32; }
+          tc_epilogue_chunk_res_tma(&tmC, &tmXB, &tmR, wst, rbar, cc, row - lane, n_blk * BN + c0, r,
+                                    g.bias ? g.bias + n_blk * BN + c0 : nullptr, lane, rb2, n02, st_s2, st_q2);
+          ++cc;
+        } else if (res_ahead) {
           int nrb = -1, nn0 = 0;
-          if (res_tma) {}
-          else if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
+          if (c0 + 32 < (chalf + 1) * COLS) { nrb = row - lane; nn0 = n_blk * BN + c0 + 32; }
           else if (tile + n_clusters < total_tiles) {
             const int nt = tile + n_clusters;
             nrb = (nt / n_tiles) * 2 * TC_BM + (int)rank * TC_BM + q * 32;
             nn0 = (nt % n_tiles) * BN + chalf * COLS;
           }
-          if (res_tma) {
-            // the chunk two ahead: same tile for the first two chunks, else the next tile's first two (nrb / nn0 above are that
-            // tile's first chunk - one division per tile, not per chunk)
-            int rb2 = -1, n02 = 0;
-            const int kc = (c0 - chalf * COLS) >> 5;
-            if (kc < 2) { rb2 = row - lane; n02 = n_blk * BN + c0 + 64; }
-            else if (nxt_tile_rb >= 0) { rb2 = nxt_tile_rb; n02 = nxt_tile_n0 + (kc - 2) * 32; }
-            tc_epilogue_chunk_res_tma(&tmC, &tmXB, &tmR, wst, rbar, cc, row - lane, n_blk * BN + c0, r,
-                                      g.bias ? g.bias + n_blk * BN + c0 : nullptr, lane, rb2, n02, st_s2, st_q2);
-            ++cc;
-          } else {
-            tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, my_stage, lane, tr2, &res, nrb, nn0, rowacc);
-          }
+          tc_epilogue_chunk(g, row, row_ok, n_blk * BN + c0, r, vb, vtok, bias_chunk, my_stage, lane, tr2, &res, nrb, nn0, rowacc);
         } else if (g.tma_store && (g.epi == TC_EPI_BF16 || n_blk * BN + c0 < 2 * g.D)) {
           tc_epilogue_chunk_bf16_tma(g, &tmC, row - lane, n_blk * BN + c0, r, bias_chunk, reinterpret_cast<uint8_t*>(my_stage), lane);
         } else {
@@ -978,8 +976,10 @@ static cudaError_t launch_tc(const GemmTc& g, int num_sms, cudaStream_t st) {
 template <int EW, int STAGES>
 static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   using Cfg2 = Tc2Cfg<EW, STAGES>;
-  static unsigned long long attr_mask = 0;
-  if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW, STAGES>, Cfg2::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
+  static unsigned long long attr_mask = 0, attr_mask_res = 0;
+  if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW, STAGES, false>, Cfg2::SMEM_BYTES, attr_mask); e != cudaSuccess) return e;
+  if constexpr (EW == 8)
+    if (cudaError_t e = opt_in_smem(gemm_tc2_kernel<EW, STAGES, true>, Cfg2::SMEM_BYTES, attr_mask_res); e != cudaSuccess) return e;
   CUtensorMap tmA, tmB;
   if (!make_map_2d(&tmA, g.A, g.M, g.K, g.lda, TC_BM)) return cudaErrorInvalidValue;
   if (!make_map_2d(&tmB, g.W, g.N, g.K, g.K, 128)) return cudaErrorInvalidValue;      // each CTA loads half of the 256 W rows
@@ -1012,7 +1012,13 @@ static cudaError_t launch_tc2(const GemmTc& g, int num_sms, cudaStream_t st) {
   const int total = ((g.M + 255) / 256) * ((g.N + 255) / 256);
   int clusters = num_sms / 2;
   if (clusters > total) clusters = total;
-  gemm_tc2_kernel<EW, STAGES><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmR, tmXB, d);
+  if constexpr (EW == 8) {
+    if (d.res_tma) {
+      gemm_tc2_kernel<EW, STAGES, true><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmR, tmXB, d);
+      return cudaGetLastError();
+    }
+  }
+  gemm_tc2_kernel<EW, STAGES, false><<<2 * clusters, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmB, tmC, tmR, tmXB, d);
   return cudaGetLastError();
 }
 
